@@ -1,0 +1,172 @@
+/*
+ * rubiks_b200.h -- C ABI of librubiks_b200.so, the B200 (sm_100a) implementation of the
+ * cube-dynamics hot path of peleiden/rl-rubiks.
+ *
+ * This is the drop-in boundary: every entry point replaces one function (or one
+ * fused group of functions) of the reference's `librubiks.cube` module API or of the hot part of
+ * `Train.ADI_traindata` / `AStar.expand_batch` / `BFS.search`.  The citation after each
+ * declaration is the reference file:line it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - Plain C types only.  `rb_*` entry points take DEVICE pointers owned by the caller (e.g. the
+ *     storage of a torch CUDA tensor) plus the CUDA stream to launch on (`rb_stream_t` is a
+ *     `cudaStream_t`; 0 = legacy default stream).  They never allocate, free or synchronise.
+ *     `rbh_*` entry points take HOST pointers, do their own staging + copies and return when the
+ *     result is in the caller's host buffer.
+ *   - Return value: RB_OK or an RB_ERR_* code; `rb_last_error()` gives a message for the calling
+ *     thread.  The reference has no error API (IndexError from numpy on bad input); the Python
+ *     mirror turns RB_ERR_RANGE into IndexError and everything else into RuntimeError.
+ *   - rep: RB_REP_2024 = the 20x24 representation (state = int8[20], one-hot width 480);
+ *     RB_REP_686 = the 6x8x6 representation (state = int8[6][8][6], one-hot width 288).
+ *   - Action index a in [0,12) <-> (face = a / 2, direction = 1 - a % 2)   (librubiks/cube/cube.py:33-35).
+ *     Where a function takes `faces` and `dirs`, `dirs` may be NULL: `faces` then holds action indices.
+ *   - All state tensors are contiguous, row-major, in the reference's own layout.
+ */
+#ifndef RUBIKS_B200_H
+#define RUBIKS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB_OK              0
+#define RB_ERR_BAD_ARG     1   /* null pointer, negative size, unknown rep / reward method */
+#define RB_ERR_CUDA        2   /* a CUDA runtime call or launch failed */
+#define RB_ERR_RANGE       3   /* rb_check_* found a face/dir/state value out of range */
+#define RB_ERR_CAPACITY    4   /* hash set full / output buffer too small */
+
+#define RB_REP_2024        0
+#define RB_REP_686         1
+
+#define RB_REWARD_PAPER      0  /* librubiks/train.py:292-296, 318-325 */
+#define RB_REWARD_LAPANFIX   1
+#define RB_REWARD_SCHULTZFIX 2
+#define RB_REWARD_REWARD0    3
+
+typedef void* rb_stream_t;      /* cudaStream_t */
+
+/* ---- library ------------------------------------------------------------------------------ */
+int         rb_version(void);
+const char* rb_last_error(void);
+/* Number of kernels this library has launched in the calling process (for bench accounting). */
+int64_t     rb_launch_count(void);
+
+/* ---- tables (librubiks/cube/maps.py:107-145 get_tensor_map; cube.py:311-326 constants) ------ */
+/* Host-side copies of the tables the kernels stage in shared memory, for inspection/tests.
+ * delta: int8[2][6][2][24] exactly as get_tensor_map returns it; lut: uint8[12][2][24] direct
+ * form lut[a][kind][s] = s + delta[dir(a)][face(a)][kind][s]; perm686: uint8[12][48] gather
+ * table new[slot] = old[perm[a][slot]] over the 48 sticker slots (slot = face*8 + ring index). */
+int rb_get_delta_maps(int8_t* delta);
+int rb_get_lut2024(uint8_t* lut);
+int rb_get_perm686(uint8_t* perm);
+/* get_solved (cube.py:58-83): writes int8[20] or int8[288] to a HOST buffer. */
+int rb_get_solved(int rep, int8_t* state);
+
+/* ---- single-step dynamics ---------------------------------------------------------------- */
+/* multi_rotate (cube.py:49-52, 257-263, 349-361): out[i] = move(faces[i], dirs[i]) on states[i]. */
+int rb_multi_rotate(int rep, const int8_t* states, const uint8_t* faces, const uint8_t* dirs,
+                    int8_t* out, int64_t n, rb_stream_t stream);
+/* multi_is_solved (cube.py:85-89): flags[i] = 1 iff states[i] equals the solved state. */
+int rb_multi_is_solved(int rep, const int8_t* states, uint8_t* flags, int64_t n, rb_stream_t stream);
+/* as_oh (cube.py:130-133, 265-277, 363-369): f32 [n][480] or [n][288], every element written. */
+int rb_as_oh(int rep, const int8_t* states, float* oh, int64_t n, rb_stream_t stream);
+/* as_correct (cube.py:135-137, 371-380): 6x8x6 only; oh f32 [n][288] -> f32 [n][6][8] of +-1. */
+int rb_as_correct_686(const float* oh, float* out, int64_t n, rb_stream_t stream);
+/* 12-neighbour expansion (cube.py:142-147 repeat_state + :179-184 iter_actions + multi_rotate, as used
+ * at train.py:285 and agents.py:277-281): child i*12+a = action a on states[i].  Any of the three
+ * outputs may be NULL: children int8 [12n][*shape], children_oh f32 [12n][W], solved uint8 [12n]. */
+int rb_expand12(int rep, const int8_t* states, int8_t* children, float* children_oh,
+                uint8_t* solved, int64_t n, rb_stream_t stream);
+/* Range check used by the Python mirror to reproduce the reference's IndexError: returns
+ * RB_ERR_RANGE if any face >= 6, dir >= 2 (or action >= 12 when dirs is NULL) or, for
+ * RB_REP_2024 with states != NULL, any state value outside [0,24).  Synchronises the stream. */
+int rb_check_range(int rep, const int8_t* states, int64_t n_states, const uint8_t* faces,
+                   const uint8_t* dirs, int64_t n_actions, int32_t* scratch_dev, rb_stream_t stream);
+
+/* ---- scramblers -------------------------------------------------------------------------- */
+/* scramble (cube.py:206-216) for n cubes at once: applies `depth` host-drawn moves to each cube,
+ * starting from `start` (int8 [n][*shape]) or from solved when start is NULL; writes the final states.
+ * Action of cube i at move m is actions[i*stride_cube + m*stride_move] (action index, 0..11), so
+ * both [n][depth] (stride_cube = depth, stride_move = 1) and [depth][n] layouts are accepted. */
+int rb_scramble(int rep, const uint8_t* actions, int64_t stride_cube, int64_t stride_move,
+                const int8_t* start, int8_t* out, int64_t n, int32_t depth, rb_stream_t stream);
+/* sequence_scrambler (cube.py:218-234) with the random draw supplied by the caller:
+ * faces/dirs uint8 [depth][games] (the reference's draw shape; dirs NULL => faces are action indices).
+ * Emits every state of every game, game-major/depth-minor; with_solved != 0 emits the solved state
+ * first and applies only rows 0..depth-2.  states int8 [games*depth][*shape], oh f32 [games*depth][W],
+ * solved uint8 [games*depth]; each may be NULL. */
+int rb_sequence_scramble(int rep, const uint8_t* faces, const uint8_t* dirs, int32_t games, int32_t depth,
+                         int32_t with_solved, int8_t* states, float* oh, uint8_t* solved, rb_stream_t stream);
+
+/* ---- ADI training batch (librubiks/train.py:256-339) --------------------------------------- */
+/* Fused generator, train.py:277-296 in one launch: sequence scramble -> 12 children of every state ->
+ * one-hot of states and of children -> solved flags of both.  n = games*depth.
+ * Outputs (NULL to skip): states int8 [n][*shape]; oh_states f32 [n][W]; children int8 [12n][*shape];
+ * children_oh f32 [12n][W]; solved_states uint8 [n]; solved_children uint8 [12n]. */
+int rb_adi_generate(int rep, const uint8_t* faces, const uint8_t* dirs, int32_t games, int32_t depth,
+                    int32_t with_solved, int8_t* states, float* oh_states, int8_t* children,
+                    float* children_oh, uint8_t* solved_states, uint8_t* solved_children, rb_stream_t stream);
+/* Target assembly, train.py:292-296 + 313-325: values f32 [12n] are the net's outputs for the children;
+ * rewards (+1 / 0 with reward0 for a solved child, -1 otherwise) are added in f32, the row argmax takes the
+ * FIRST maximum (NaN counts as maximum, as torch.argmax), lapanfix zeroes targets of solved states,
+ * schultzfix zeroes rows 0, depth, 2*depth, ...  policy int64 [n], value f32 [n]. */
+int rb_adi_targets(const float* values, const uint8_t* solved_children, const uint8_t* solved_states,
+                   int64_t n, int32_t depth, int32_t reward_method, int64_t* policy, float* value,
+                   rb_stream_t stream);
+/* Loss weights, train.py:329-333, evaluated in f64 and rounded to f32 like the reference:
+ * ((1-alpha) w/ws + alpha/N)(ws+N), w = 1/(1 + i % depth), N = games*depth.  `ws` is the f64 sum of w the
+ * caller obtained the reference's way (numpy pairwise sum; rb_adi_weight_sum restates it). */
+double rb_adi_weight_sum(int32_t games, int32_t depth);
+int rb_adi_loss_weights(float* out, int32_t games, int32_t depth, double alpha, double ws, rb_stream_t stream);
+
+/* ---- search frontier: seen-set on the packed state (agents.py:103-121, 286-306, 517-526, 605-609) --- */
+/* Open-addressing hash set keyed on the packed state, 128 bit: 20x24 -> 20 cubies x 5 bit = 100 bit;
+ * 6x8x6 -> the 8 sticker colours of each face as a base-6 number (6^8 < 2^21), 6 x 21 = 126 bit, injective on
+ * valid one-hot states (the only ones a cube can reach).
+ * The table lives in caller-owned device memory of rb_hashset_bytes(capacity) bytes; capacity must be a
+ * power of two.  The set maps state -> index (int32, 1-based in insertion order like the reference's
+ * `indices` dict; 0 = absent). */
+int64_t rb_hashset_bytes(int64_t capacity);
+int rb_hashset_clear(void* table, int64_t capacity, rb_stream_t stream);
+/* Growth: clears `dst` (dst_capacity >= src_capacity) and re-inserts every (state key, index) pair of `src`. */
+int rb_hashset_rehash(void* src, int64_t src_capacity, void* dst, int64_t dst_capacity, rb_stream_t stream);
+/* Batch insert with the reference's order semantics (agents.py:286-306): for states[0..n) in order,
+ * seen[i] = state was in the set before this call; first[i] = i is the first occurrence of its state in this
+ * batch; index[i] = index of the state after the call, new states (first & ~seen) numbered count+1, count+2, ...
+ * in batch order.  `count_dev` (int32 on device) holds the set size and is updated; no host sync.
+ * scratch: caller-owned device buffer of rb_hashset_scratch_bytes(n) bytes. */
+int64_t rb_hashset_scratch_bytes(int64_t n);
+int rb_hashset_insert_unique(int rep, void* table, int64_t capacity, const int8_t* states, int64_t n,
+                             int32_t* count_dev, uint8_t* seen, uint8_t* first, int32_t* index,
+                             void* scratch, rb_stream_t stream);
+/* Lookup only (agents.py:606-607 `_complete_graph`): index[i] or 0 when absent.  scratch: as for insert
+ * (needed for RB_REP_686 only; may be NULL for RB_REP_2024). */
+int rb_hashset_lookup(int rep, const void* table, int64_t capacity, const int8_t* states, int64_t n,
+                      int32_t* index, void* scratch, rb_stream_t stream);
+/* One layer of breadth-first search (BFS.search agents.py:96-123 made layer-synchronous; the frontier part of
+ * AStar.expand_batch agents.py:272-307): expands frontier[0..n) to 12n children, inserts them with
+ * rb_hashset_insert_unique semantics and compacts the new ones, in batch order, to
+ * next_frontier (int8 [<=12n][*shape]) with their parent position and action (parent int32, action uint8;
+ * NULL to skip) and solved flag.  n_new_dev (int32, device) receives the number of new states. */
+int rb_frontier_expand(int rep, void* table, int64_t capacity, const int8_t* frontier, int64_t n,
+                       int32_t* count_dev, int8_t* next_frontier, int32_t* parent, uint8_t* action,
+                       uint8_t* solved, uint8_t* seen, uint8_t* first, int32_t* index, int32_t* n_new_dev,
+                       void* scratch, rb_stream_t stream);
+int64_t rb_frontier_scratch_bytes(int rep, int64_t n);
+
+/* ---- host-buffer entry points (end-to-end: H2D + kernels + D2H inside the call) --------------- */
+/* rb_scramble on host buffers; actions uint8 [n][depth] (cube-major), out int8 [n][*shape].  Copies are
+ * chunked and double-buffered on internal streams; pinned host memory makes them asynchronous. */
+int rbh_scramble(int rep, const uint8_t* actions, int8_t* out, int64_t n, int32_t depth);
+/* multi_rotate on host buffers (the reference's own call shape: numpy in, numpy out). */
+int rbh_multi_rotate(int rep, const int8_t* states, const uint8_t* faces, const uint8_t* dirs,
+                     int8_t* out, int64_t n);
+/* Release cached device staging buffers held by the rbh_* entry points. */
+int rbh_release(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RUBIKS_B200_H */

@@ -1,0 +1,264 @@
+// 6x8x6 representation kernels.  A state is int8[6][8][6] = 48 sticker slots x 6-byte colour one-hot
+// (288 B, 72 words, 18 x 16 B).  Every move is a fixed permutation of the 48 slots that moves exactly 20 of
+// them (reference: librubiks/cube/cube.py:330-361); the kernels move whole 6-byte records, so any int8
+// content is carried bit-exactly, as the reference's fancy-index assignment does.
+#pragma once
+#include "rb_common.cuh"
+
+namespace rb686 {
+
+constexpr int kThreads = 256;
+constexpr int kStateBytes = 288;
+constexpr int kTile = 64;               // states per tile: 18 KB in + 18 KB out of shared memory
+constexpr int kSlots = 48;
+
+__device__ __forceinline__ void stage_perm(uint8_t* s_perm) {
+	for (int i = threadIdx.x; i < 12 * 48 / 16; i += blockDim.x)
+		reinterpret_cast<uint4*>(s_perm)[i] = reinterpret_cast<const uint4*>(g_perm686)[i];
+}
+
+// Copy one 6-byte sticker record inside shared memory (2-byte aligned).
+__device__ __forceinline__ void copy_record(uint8_t* dst, const uint8_t* src) {
+	const uint16_t* s = reinterpret_cast<const uint16_t*>(src);
+	uint16_t* d = reinterpret_cast<uint16_t*>(dst);
+	const uint16_t a = s[0], b = s[1], c = s[2];
+	d[0] = a; d[1] = b; d[2] = c;
+}
+
+// multi_rotate: 288 B in + action + 288 B out per state; tiles staged through shared memory with 16-byte
+// coalesced global accesses, the permutation applied record by record (thread = one slot of one state).
+__global__ void __launch_bounds__(kThreads)
+k_multi_rotate(const int8_t* __restrict__ in, const uint8_t* __restrict__ faces, const uint8_t* __restrict__ dirs,
+               int8_t* __restrict__ out, int64_t n) {
+	__shared__ __align__(16) uint8_t s_perm[12 * 48];
+	__shared__ __align__(16) uint8_t s_in[kTile * kStateBytes];
+	__shared__ __align__(16) uint8_t s_out[kTile * kStateBytes];
+	__shared__ uint8_t s_act[kTile];
+	stage_perm(s_perm);
+	const int64_t n_tiles = (n + kTile - 1) / kTile;
+	for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+		const int64_t base = tile * kTile;
+		const int cnt = (int)min((int64_t)kTile, n - base);
+		__syncthreads();
+		rb_g2s(s_in, reinterpret_cast<const uint8_t*>(in) + base * kStateBytes, cnt * kStateBytes);
+		if (threadIdx.x < cnt)
+			s_act[threadIdx.x] = (uint8_t)(dirs ? rb_action_of(faces[base + threadIdx.x], dirs[base + threadIdx.x])
+			                                    : rb_clamp_action(faces[base + threadIdx.x]));
+		__syncthreads();
+		for (int t = threadIdx.x; t < cnt * kSlots; t += kThreads) {
+			const int st = t / kSlots, slot = t - st * kSlots;
+			const int src = s_perm[s_act[st] * kSlots + slot];
+			copy_record(s_out + st * kStateBytes + slot * 6, s_in + st * kStateBytes + src * 6);
+		}
+		__syncthreads();
+		rb_s2g(reinterpret_cast<uint8_t*>(out) + base * kStateBytes, s_out, cnt * kStateBytes);
+	}
+}
+
+// multi_is_solved: compare 72 words per state against the solved state; warp per state.
+__global__ void __launch_bounds__(kThreads)
+k_is_solved(const int8_t* __restrict__ in, uint8_t* __restrict__ flags, int64_t n) {
+	const int lane = threadIdx.x & 31;
+	const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+	const int64_t n_warps = (int64_t)gridDim.x * (kThreads / 32);
+	const uint32_t* sv = reinterpret_cast<const uint32_t*>(g_solved686);
+	for (int64_t i = warp; i < n; i += n_warps) {
+		const uint32_t* p = reinterpret_cast<const uint32_t*>(in + i * kStateBytes);
+		bool ok = true;
+#pragma unroll
+		for (int k = 0; k < 3; ++k) {
+			const int w = lane + 32 * k;
+			if (w < 72) ok &= (p[w] == sv[w]);
+		}
+		ok = __all_sync(0xffffffffu, ok);
+		if (lane == 0) flags[i] = ok;
+	}
+}
+
+// as_oh: int8 -> f32 widening of the already one-hot state: 288 B in, 1152 B out.  Thread = 4 bytes -> float4.
+__global__ void __launch_bounds__(kThreads)
+k_as_oh(const int8_t* __restrict__ in, float* __restrict__ oh, int64_t n_words) {
+	const uint32_t* src = reinterpret_cast<const uint32_t*>(in);
+	float4* dst = reinterpret_cast<float4*>(oh);
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (int64_t)gridDim.x * blockDim.x) {
+		const uint32_t w = src[i];
+		float4 o;
+		o.x = (float)(int8_t)(w & 0xff);
+		o.y = (float)(int8_t)((w >> 8) & 0xff);
+		o.z = (float)(int8_t)((w >> 16) & 0xff);
+		o.w = (float)(int8_t)(w >> 24);
+		rb_st_stream(dst + i, o);
+	}
+}
+
+// as_correct (cube.py:371-380): f32 [n][288] -> f32 [n][48]: +1 where the sticker's 6 channels equal the solved
+// sticker's, else -1.  Thread = one sticker.
+__global__ void __launch_bounds__(kThreads)
+k_as_correct(const float* __restrict__ oh, float* __restrict__ out, int64_t n_slots) {
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (int64_t)gridDim.x * blockDim.x) {
+		const int slot = (int)(i % kSlots);
+		const float2* p = reinterpret_cast<const float2*>(oh + i * 6);
+		bool ok = true;
+#pragma unroll
+		for (int k = 0; k < 3; ++k) {
+			const float2 q = p[k];
+			ok &= (q.x == (float)g_solved686[slot * 6 + 2 * k]) & (q.y == (float)g_solved686[slot * 6 + 2 * k + 1]);
+		}
+		out[i] = ok ? 1.f : -1.f;
+	}
+}
+
+// Emit one state held in shared memory (288 B at `s`): raw bytes, f32 one-hot row and solved flag; warp-wide.
+__device__ __forceinline__ void warp_emit(const uint8_t* s, int lane, int64_t row, int8_t* __restrict__ states,
+                                          float* __restrict__ oh, uint8_t* __restrict__ solved) {
+	if (states && lane < 18)
+		rb_st_stream(reinterpret_cast<uint4*>(states + row * kStateBytes) + lane, reinterpret_cast<const uint4*>(s)[lane]);
+	if (oh) {
+		float4* dst = reinterpret_cast<float4*>(oh + row * kStateBytes);
+#pragma unroll
+		for (int k = 0; k < 3; ++k) {
+			const int w = lane + 32 * k;
+			if (w < 72) {
+				const uint32_t x = reinterpret_cast<const uint32_t*>(s)[w];
+				float4 o;
+				o.x = (float)(int8_t)(x & 0xff);
+				o.y = (float)(int8_t)((x >> 8) & 0xff);
+				o.z = (float)(int8_t)((x >> 16) & 0xff);
+				o.w = (float)(int8_t)(x >> 24);
+				rb_st_stream(dst + w, o);
+			}
+		}
+	}
+	if (solved) {
+		bool ok = true;
+#pragma unroll
+		for (int k = 0; k < 3; ++k) {
+			const int w = lane + 32 * k;
+			if (w < 72) ok &= reinterpret_cast<const uint32_t*>(s)[w] == reinterpret_cast<const uint32_t*>(g_solved686)[w];
+		}
+		ok = __all_sync(0xffffffffu, ok);
+		if (lane == 0) solved[row] = ok;
+	}
+}
+
+// dst = move a applied to src (both 288 B in shared memory, distinct buffers); warp-wide.
+__device__ __forceinline__ void warp_move(uint8_t* dst, const uint8_t* src, const uint8_t* s_perm, uint32_t a, int lane) {
+	for (int slot = lane; slot < kSlots; slot += 32)
+		copy_record(dst + slot * 6, src + s_perm[a * kSlots + slot] * 6);
+	__syncwarp();
+}
+
+constexpr int kWarps = kThreads / 32;
+
+// expand12 (+ one-hot + solved): warp per parent; parent and one child buffer per warp in shared memory.
+__device__ __forceinline__ void warp_expand12(uint8_t* child, const uint8_t* parent, const uint8_t* s_perm, int lane,
+                                              int64_t prow, int8_t* __restrict__ children, float* __restrict__ children_oh,
+                                              uint8_t* __restrict__ solved) {
+	for (uint32_t a = 0; a < 12; ++a) {
+		warp_move(child, parent, s_perm, a, lane);
+		warp_emit(child, lane, prow * 12 + a, children, children_oh, solved);
+		__syncwarp();
+	}
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_expand12(const int8_t* __restrict__ in, int8_t* __restrict__ children, float* __restrict__ children_oh,
+           uint8_t* __restrict__ solved, int64_t n) {
+	__shared__ __align__(16) uint8_t s_perm[12 * 48];
+	__shared__ __align__(16) uint8_t s_buf[kWarps][2][kStateBytes];
+	stage_perm(s_perm);
+	__syncthreads();
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const int64_t warp = (int64_t)blockIdx.x * kWarps + wib;
+	const int64_t n_warps = (int64_t)gridDim.x * kWarps;
+	for (int64_t i = warp; i < n; i += n_warps) {
+		if (lane < 18)
+			reinterpret_cast<uint4*>(s_buf[wib][0])[lane] = rb_ld_stream(reinterpret_cast<const uint4*>(in + i * kStateBytes) + lane);
+		__syncwarp();
+		warp_expand12(s_buf[wib][1], s_buf[wib][0], s_perm, lane, i, children, children_oh, solved);
+	}
+}
+
+// scramble: `depth` moves per cube, final state only; warp per cube, ping-pong buffers in shared memory.
+__global__ void __launch_bounds__(kThreads)
+k_scramble(const uint8_t* __restrict__ actions, int64_t stride_cube, int64_t stride_move,
+           const int8_t* __restrict__ start, int8_t* __restrict__ out, int64_t n, int depth) {
+	__shared__ __align__(16) uint8_t s_perm[12 * 48];
+	__shared__ __align__(16) uint8_t s_buf[kWarps][2][kStateBytes];
+	stage_perm(s_perm);
+	__syncthreads();
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const int64_t warp = (int64_t)blockIdx.x * kWarps + wib;
+	const int64_t n_warps = (int64_t)gridDim.x * kWarps;
+	for (int64_t i = warp; i < n; i += n_warps) {
+		const uint8_t* src = start ? reinterpret_cast<const uint8_t*>(start) + i * kStateBytes : g_solved686;
+		if (lane < 18) reinterpret_cast<uint4*>(s_buf[wib][0])[lane] = reinterpret_cast<const uint4*>(src)[lane];
+		__syncwarp();
+		int cur = 0;
+		for (int m0 = 0; m0 < depth; m0 += 32) {
+			const int m = m0 + lane;
+			const uint32_t a_l = m < depth ? rb_clamp_action(actions[i * stride_cube + (int64_t)m * stride_move]) : 0u;
+			const int stop = min(32, depth - m0);
+			for (int k = 0; k < stop; ++k) {
+				warp_move(s_buf[wib][cur ^ 1], s_buf[wib][cur], s_perm, __shfl_sync(0xffffffffu, a_l, k), lane);
+				cur ^= 1;
+			}
+		}
+		if (lane < 18)
+			rb_st_stream(reinterpret_cast<uint4*>(out + i * kStateBytes) + lane, reinterpret_cast<const uint4*>(s_buf[wib][cur])[lane]);
+		__syncwarp();
+	}
+}
+
+// sequence_scramble / fused ADI generator: same unit decomposition as the 20x24 kernel (game, chunk of depth).
+template <bool kChildren>
+__global__ void __launch_bounds__(kThreads)
+k_sequence(const uint8_t* __restrict__ faces, const uint8_t* __restrict__ dirs, int games, int depth,
+           int with_solved, int chunk, int8_t* __restrict__ states, float* __restrict__ oh,
+           uint8_t* __restrict__ solved_states, int8_t* __restrict__ children, float* __restrict__ children_oh,
+           uint8_t* __restrict__ solved_children) {
+	__shared__ __align__(16) uint8_t s_perm[12 * 48];
+	__shared__ __align__(16) uint8_t s_buf[kWarps][3][kStateBytes];
+	stage_perm(s_perm);
+	__syncthreads();
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const int chunks_per_game = (depth + chunk - 1) / chunk;
+	const int64_t n_units = (int64_t)games * chunks_per_game;
+	const int64_t warp = (int64_t)blockIdx.x * kWarps + wib;
+	const int64_t n_warps = (int64_t)gridDim.x * kWarps;
+	for (int64_t u = warp; u < n_units; u += n_warps) {
+		const int g = (int)(u / chunks_per_game);
+		const int d0 = (int)(u % chunks_per_game) * chunk;
+		const int d1 = min(depth, d0 + chunk);
+		if (lane < 18) reinterpret_cast<uint4*>(s_buf[wib][0])[lane] = reinterpret_cast<const uint4*>(g_solved686)[lane];
+		__syncwarp();
+		int cur = 0;
+		const int total = d1 - with_solved;
+		int applied = 0, buf0 = 0;
+		uint32_t a_l = 0;
+		auto fetch = [&]() {
+			const int m = buf0 + lane;
+			a_l = 0;
+			if (m < total) {
+				const int64_t idx = (int64_t)m * games + g;
+				a_l = dirs ? rb_action_of(faces[idx], dirs[idx]) : rb_clamp_action(faces[idx]);
+			}
+		};
+		fetch();
+		for (int d = d0; d < d1; ++d) {
+			const int want = d + 1 - with_solved;
+			while (applied < want) {
+				if (applied - buf0 == 32) { buf0 = applied; fetch(); }
+				warp_move(s_buf[wib][cur ^ 1], s_buf[wib][cur], s_perm, __shfl_sync(0xffffffffu, a_l, applied - buf0), lane);
+				cur ^= 1;
+				++applied;
+			}
+			const int64_t row = (int64_t)g * depth + d;
+			warp_emit(s_buf[wib][cur], lane, row, states, oh, solved_states);
+			if (kChildren) warp_expand12(s_buf[wib][2], s_buf[wib][cur], s_perm, lane, row, children, children_oh, solved_children);
+			__syncwarp();
+		}
+	}
+}
+
+}  // namespace rb686

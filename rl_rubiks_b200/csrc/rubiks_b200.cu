@@ -1,0 +1,458 @@
+// librubiks_b200.so -- C ABI (include/rubiks_b200.h) over the sm_100a kernels.  Single translation unit.
+#include "rb_common.cuh"
+#include "rb_tables.cuh"
+#include "rb_cube2024.cuh"
+#include "rb_cube686.cuh"
+#include "rb_adi.cuh"
+#include "rb_frontier.cuh"
+#include "rb_host.cuh"
+
+#define RB_INIT()                                   \
+	do {                                            \
+		int rc_ = rbt::ensure_device();             \
+		if (rc_ != RB_OK) return rc_;               \
+	} while (0)
+
+static inline bool aligned(const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+static inline cudaStream_t S(rb_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline bool rep_ok(int rep) { return rep == RB_REP_2024 || rep == RB_REP_686; }
+
+extern "C" {
+
+int rb_version(void) { return 100; }
+const char* rb_last_error(void) { return g_rb_err; }
+int64_t rb_launch_count(void) { return g_rb_launches.load(); }
+
+int rb_get_delta_maps(int8_t* delta) {
+	RB_REQUIRE(delta, "null output");
+	memcpy(delta, rbt::host().delta, sizeof(rbt::host().delta));
+	return RB_OK;
+}
+int rb_get_lut2024(uint8_t* lut) {
+	RB_REQUIRE(lut, "null output");
+	memcpy(lut, rbt::host().lut, sizeof(rbt::host().lut));
+	return RB_OK;
+}
+int rb_get_perm686(uint8_t* perm) {
+	RB_REQUIRE(perm, "null output");
+	memcpy(perm, rbt::host().perm686, sizeof(rbt::host().perm686));
+	return RB_OK;
+}
+int rb_get_solved(int rep, int8_t* state) {
+	RB_REQUIRE(state && rep_ok(rep), "bad argument");
+	if (rep == RB_REP_2024) memcpy(state, rbt::host().solved2024, 20);
+	else memcpy(state, rbt::host().solved686, 288);
+	return RB_OK;
+}
+
+int rb_multi_rotate(int rep, const int8_t* states, const uint8_t* faces, const uint8_t* dirs, int8_t* out,
+                    int64_t n, rb_stream_t stream) {
+	RB_REQUIRE(rep_ok(rep) && n >= 0, "bad rep or size");
+	if (n == 0) return RB_OK;
+	RB_REQUIRE(states && faces && out, "null pointer");
+	RB_INIT();
+	if (rep == RB_REP_2024) {
+		rb2024::k_multi_rotate<<<rb_grid(n, rb2024::kTile, 2), rb2024::kThreads, 0, S(stream)>>>(states, faces, dirs, out, n);
+		RB_LAUNCHED("multi_rotate_2024");
+	} else {
+		rb686::k_multi_rotate<<<rb_grid(n, rb686::kTile, 4), rb686::kThreads, 0, S(stream)>>>(states, faces, dirs, out, n);
+		RB_LAUNCHED("multi_rotate_686");
+	}
+	return RB_OK;
+}
+
+int rb_multi_is_solved(int rep, const int8_t* states, uint8_t* flags, int64_t n, rb_stream_t stream) {
+	RB_REQUIRE(rep_ok(rep) && n >= 0, "bad rep or size");
+	if (n == 0) return RB_OK;
+	RB_REQUIRE(states && flags, "null pointer");
+	RB_INIT();
+	if (rep == RB_REP_2024) {
+		rb2024::k_is_solved<<<rb_grid(n, rb2024::kTile, 2), rb2024::kThreads, 0, S(stream)>>>(states, flags, n);
+		RB_LAUNCHED("is_solved_2024");
+	} else {
+		RB_REQUIRE(aligned(states, 4), "6x8x6 states must be 4-byte aligned");
+		rb686::k_is_solved<<<rb_grid(n, rb686::kWarps, 8), rb686::kThreads, 0, S(stream)>>>(states, flags, n);
+		RB_LAUNCHED("is_solved_686");
+	}
+	return RB_OK;
+}
+
+int rb_as_oh(int rep, const int8_t* states, float* oh, int64_t n, rb_stream_t stream) {
+	RB_REQUIRE(rep_ok(rep) && n >= 0, "bad rep or size");
+	if (n == 0) return RB_OK;
+	RB_REQUIRE(states && oh, "null pointer");
+	RB_REQUIRE(aligned(oh, 16), "one-hot output must be 16-byte aligned");
+	RB_INIT();
+	if (rep == RB_REP_2024) {
+		rb2024::k_as_oh<<<rb_grid(n, 8, 8), rb2024::kThreads, 0, S(stream)>>>(states, oh, n);
+		RB_LAUNCHED("as_oh_2024");
+	} else {
+		RB_REQUIRE(aligned(states, 4), "6x8x6 states must be 4-byte aligned");
+		rb686::k_as_oh<<<rb_grid(n * 72, rb686::kThreads * 4, 8), rb686::kThreads, 0, S(stream)>>>(states, oh, n * 72);
+		RB_LAUNCHED("as_oh_686");
+	}
+	return RB_OK;
+}
+
+int rb_as_correct_686(const float* oh, float* out, int64_t n, rb_stream_t stream) {
+	RB_REQUIRE(n >= 0, "bad size");
+	if (n == 0) return RB_OK;
+	RB_REQUIRE(oh && out && aligned(oh, 8), "null or misaligned pointer");
+	RB_INIT();
+	rb686::k_as_correct<<<rb_grid(n * 48, rb686::kThreads, 8), rb686::kThreads, 0, S(stream)>>>(oh, out, n * 48);
+	RB_LAUNCHED("as_correct_686");
+	return RB_OK;
+}
+
+int rb_expand12(int rep, const int8_t* states, int8_t* children, float* children_oh, uint8_t* solved, int64_t n,
+                rb_stream_t stream) {
+	RB_REQUIRE(rep_ok(rep) && n >= 0, "bad rep or size");
+	if (n == 0) return RB_OK;
+	RB_REQUIRE(states && (children || children_oh || solved), "null pointer");
+	RB_REQUIRE(aligned(children_oh, 16), "one-hot output must be 16-byte aligned");
+	RB_INIT();
+	if (rep == RB_REP_2024) {
+		rb2024::k_expand12<<<rb_grid(n, 8, 8), rb2024::kThreads, 0, S(stream)>>>(states, children, children_oh, solved, n);
+		RB_LAUNCHED("expand12_2024");
+	} else {
+		RB_REQUIRE(aligned(states, 16) && aligned(children, 16), "6x8x6 states must be 16-byte aligned");
+		rb686::k_expand12<<<rb_grid(n, rb686::kWarps, 6), rb686::kThreads, 0, S(stream)>>>(states, children, children_oh, solved, n);
+		RB_LAUNCHED("expand12_686");
+	}
+	return RB_OK;
+}
+
+int rb_scramble(int rep, const uint8_t* actions, int64_t stride_cube, int64_t stride_move, const int8_t* start,
+                int8_t* out, int64_t n, int32_t depth, rb_stream_t stream) {
+	RB_REQUIRE(rep_ok(rep) && n >= 0 && depth >= 0, "bad rep or size");
+	if (n == 0) return RB_OK;
+	RB_REQUIRE(out && (actions || depth == 0), "null pointer");
+	RB_INIT();
+	if (rep == RB_REP_2024) {
+		rb2024::k_scramble<<<rb_grid(n, rb2024::kThreads, 8), rb2024::kThreads, 0, S(stream)>>>(
+			actions, stride_cube, stride_move, start, out, n, depth);
+		RB_LAUNCHED("scramble_2024");
+	} else {
+		RB_REQUIRE(aligned(out, 16) && aligned(start, 16), "6x8x6 states must be 16-byte aligned");
+		rb686::k_scramble<<<rb_grid(n, rb686::kWarps, 6), rb686::kThreads, 0, S(stream)>>>(
+			actions, stride_cube, stride_move, start, out, n, depth);
+		RB_LAUNCHED("scramble_686");
+	}
+	return RB_OK;
+}
+
+static int sequence_chunk(int64_t games, int depth) {
+	// enough (game, chunk) units for ~8 warps x 8 blocks per SM, but never replay more than needed
+	int64_t target_units = (int64_t)RB_NUM_SMS * 64;
+	int64_t chunks_per_game = (target_units + games - 1) / games;
+	if (chunks_per_game < 1) chunks_per_game = 1;
+	if (chunks_per_game > depth) chunks_per_game = depth;
+	return (int)((depth + chunks_per_game - 1) / chunks_per_game);
+}
+
+static int launch_sequence(int rep, bool with_children, const uint8_t* faces, const uint8_t* dirs, int32_t games,
+                           int32_t depth, int32_t with_solved, int8_t* states, float* oh, uint8_t* solved_states,
+                           int8_t* children, float* children_oh, uint8_t* solved_children, rb_stream_t stream) {
+	RB_REQUIRE(rep_ok(rep) && games >= 0 && depth >= 0, "bad rep or size");
+	if (games == 0 || depth == 0) return RB_OK;
+	RB_REQUIRE(faces || (depth == 1 && with_solved), "null action pointer");
+	RB_REQUIRE(aligned(oh, 16) && aligned(children_oh, 16), "one-hot outputs must be 16-byte aligned");
+	RB_INIT();
+	const int ws = with_solved ? 1 : 0;
+	const int chunk = sequence_chunk(games, depth);
+	const int64_t units = (int64_t)games * ((depth + chunk - 1) / chunk);
+	if (rep == RB_REP_2024) {
+		const int grid = rb_grid(units, 8, 8);
+		if (with_children)
+			rb2024::k_sequence<true><<<grid, rb2024::kThreads, 0, S(stream)>>>(faces, dirs, games, depth, ws, chunk, states, oh,
+			                                                               solved_states, children, children_oh, solved_children);
+		else
+			rb2024::k_sequence<false><<<grid, rb2024::kThreads, 0, S(stream)>>>(faces, dirs, games, depth, ws, chunk, states, oh,
+			                                                                solved_states, nullptr, nullptr, nullptr);
+		RB_LAUNCHED("sequence_2024");
+	} else {
+		RB_REQUIRE(aligned(states, 16) && aligned(children, 16), "6x8x6 states must be 16-byte aligned");
+		const int grid = rb_grid(units, rb686::kWarps, 6);
+		if (with_children)
+			rb686::k_sequence<true><<<grid, rb686::kThreads, 0, S(stream)>>>(faces, dirs, games, depth, ws, chunk, states, oh,
+			                                                              solved_states, children, children_oh, solved_children);
+		else
+			rb686::k_sequence<false><<<grid, rb686::kThreads, 0, S(stream)>>>(faces, dirs, games, depth, ws, chunk, states, oh,
+			                                                               solved_states, nullptr, nullptr, nullptr);
+		RB_LAUNCHED("sequence_686");
+	}
+	return RB_OK;
+}
+
+int rb_sequence_scramble(int rep, const uint8_t* faces, const uint8_t* dirs, int32_t games, int32_t depth,
+                         int32_t with_solved, int8_t* states, float* oh, uint8_t* solved, rb_stream_t stream) {
+	return launch_sequence(rep, false, faces, dirs, games, depth, with_solved, states, oh, solved, nullptr, nullptr, nullptr, stream);
+}
+
+int rb_adi_generate(int rep, const uint8_t* faces, const uint8_t* dirs, int32_t games, int32_t depth, int32_t with_solved,
+                    int8_t* states, float* oh_states, int8_t* children, float* children_oh, uint8_t* solved_states,
+                    uint8_t* solved_children, rb_stream_t stream) {
+	return launch_sequence(rep, true, faces, dirs, games, depth, with_solved, states, oh_states, solved_states, children,
+	                       children_oh, solved_children, stream);
+}
+
+int rb_adi_targets(const float* values, const uint8_t* solved_children, const uint8_t* solved_states, int64_t n,
+                   int32_t depth, int32_t reward_method, int64_t* policy, float* value, rb_stream_t stream) {
+	RB_REQUIRE(n >= 0 && depth > 0, "bad size");
+	RB_REQUIRE(reward_method >= RB_REWARD_PAPER && reward_method <= RB_REWARD_REWARD0, "unknown reward method");
+	if (n == 0) return RB_OK;
+	RB_REQUIRE(values && solved_children && policy && value, "null pointer");
+	RB_REQUIRE(reward_method != RB_REWARD_LAPANFIX || solved_states, "lapanfix needs solved_states");
+	RB_REQUIRE(aligned(values, 16) && aligned(solved_children, 4), "values must be 16-byte and flags 4-byte aligned");
+	rbadi::k_targets<<<rb_grid(n, rbadi::kThreads, 8), rbadi::kThreads, 0, S(stream)>>>(values, solved_children, solved_states, n,
+	                                                                             depth, reward_method, policy, value);
+	RB_LAUNCHED("adi_targets");
+	return RB_OK;
+}
+
+double rb_adi_weight_sum(int32_t games, int32_t depth) {
+	if (games <= 0 || depth <= 0) return 0.0;
+	const int64_t n = (int64_t)games * depth;
+	double* w = new double[n];
+	for (int64_t i = 0; i < n; ++i) w[i] = 1.0 / (double)(1 + i % depth);
+	const double s = rbadi::pairwise_sum(w, n);
+	delete[] w;
+	return s;
+}
+
+int rb_adi_loss_weights(float* out, int32_t games, int32_t depth, double alpha, double ws, rb_stream_t stream) {
+	RB_REQUIRE(games >= 0 && depth >= 0, "bad size");
+	const int64_t n = (int64_t)games * depth;
+	if (n == 0) return RB_OK;
+	RB_REQUIRE(out, "null pointer");
+	rbadi::k_loss_weights<<<rb_grid(n, rbadi::kThreads, 8), rbadi::kThreads, 0, S(stream)>>>(out, n, depth, alpha, ws);
+	RB_LAUNCHED("adi_loss_weights");
+	return RB_OK;
+}
+
+// ---- search frontier ----------------------------------------------------------------------------------------
+int64_t rb_hashset_bytes(int64_t capacity) { return capacity > 0 ? capacity * 24 : 0; }
+
+static bool pow2(int64_t x) { return x > 0 && (x & (x - 1)) == 0; }
+
+int rb_hashset_clear(void* table, int64_t capacity, rb_stream_t stream) {
+	RB_REQUIRE(table && pow2(capacity) && aligned(table, 16), "table must be 16-byte aligned with a power-of-two capacity");
+	rbf::k_clear<<<rb_grid(capacity, rbf::kThreads * 4, 8), rbf::kThreads, 0, S(stream)>>>(table, capacity);
+	RB_LAUNCHED("hashset_clear");
+	return RB_OK;
+}
+
+int rb_hashset_rehash(void* src, int64_t src_capacity, void* dst, int64_t dst_capacity, rb_stream_t stream) {
+	RB_REQUIRE(src && dst && pow2(src_capacity) && pow2(dst_capacity) && dst_capacity >= src_capacity && aligned(src, 16) && aligned(dst, 16),
+	           "bad tables");
+	int rc = rb_hashset_clear(dst, dst_capacity, stream);
+	if (rc != RB_OK) return rc;
+	rbf::k_rehash<<<rb_grid(src_capacity, rbf::kThreads * 4, 8), rbf::kThreads, 0, S(stream)>>>(src, src_capacity, dst, dst_capacity);
+	RB_LAUNCHED("hashset_rehash");
+	return RB_OK;
+}
+
+int64_t rb_hashset_scratch_bytes(int64_t n) { return n >= 0 ? rbf::scratch_bytes(n, true) : 0; }
+
+int64_t rb_frontier_scratch_bytes(int rep, int64_t n) {
+	if (n < 0) return 0;
+	const int64_t items = 12 * n;
+	int64_t b = rbf::scratch_bytes(items, rep == RB_REP_686);
+	if (rep == RB_REP_686) b += items * 288 + ((items + 3) / 4) * 16;     // children + new item ids
+	return b;
+}
+
+// probe -> flag -> scan -> (assign by caller) shared by insert_unique and frontier_expand
+static int frontier_common_tail(void* table, int64_t capacity, int64_t items, const rbf::Scratch& sc, uint8_t* seen,
+                                uint8_t* first, cudaStream_t st) {
+	rbf::k_flag<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(table, capacity, items, sc.slot, seen, first, sc.block_new);
+	RB_LAUNCHED("frontier_flag");
+	rbf::k_scan<<<1, 1024, 0, st>>>(sc.block_new, sc.nb);
+	RB_LAUNCHED("frontier_scan");
+	return RB_OK;
+}
+
+int rb_hashset_insert_unique(int rep, void* table, int64_t capacity, const int8_t* states, int64_t n, int32_t* count_dev,
+                             uint8_t* seen, uint8_t* first, int32_t* index, void* scratch, rb_stream_t stream) {
+	RB_REQUIRE(rep_ok(rep) && n >= 0 && n < (1ll << 31), "bad rep or size");
+	if (n == 0) return RB_OK;
+	RB_REQUIRE(table && pow2(capacity) && aligned(table, 16) && states && count_dev && scratch && aligned(scratch, 16), "bad table or pointers");
+	RB_INIT();
+	const rbf::Scratch sc = rbf::scratch_of(scratch, n);
+	cudaStream_t st = S(stream);
+	if (rep == RB_REP_2024) {
+		rbf::k_probe2024<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(rbf::FromArray2024{states}, table, capacity, n, sc.slot);
+		RB_LAUNCHED("frontier_probe_2024");
+	} else {
+		RB_REQUIRE(aligned(states, 4), "6x8x6 states must be 4-byte aligned");
+		rbf::k_pack686<<<(unsigned)((n + 7) / 8), rbf::kThreads, 0, st>>>(states, n, sc.keys);
+		RB_LAUNCHED("frontier_pack_686");
+		rbf::k_probe_keys<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(sc.keys, table, capacity, n, sc.slot);
+		RB_LAUNCHED("frontier_probe_keys");
+	}
+	int rc = frontier_common_tail(table, capacity, n, sc, seen, first, st);
+	if (rc != RB_OK) return rc;
+	rbf::k_assign_ids<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(table, capacity, n, sc.slot, sc.block_new, count_dev, nullptr);
+	RB_LAUNCHED("frontier_assign");
+	rbf::k_finish<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(table, capacity, n, sc.slot, index);
+	RB_LAUNCHED("frontier_finish");
+	rbf::k_bump<<<1, 1, 0, st>>>(count_dev, sc.block_new, sc.nb, nullptr);
+	RB_LAUNCHED("frontier_bump");
+	return RB_OK;
+}
+
+int rb_hashset_lookup(int rep, const void* table, int64_t capacity, const int8_t* states, int64_t n, int32_t* index,
+                      void* scratch, rb_stream_t stream) {
+	RB_REQUIRE(rep_ok(rep) && n >= 0 && n < (1ll << 31), "bad rep or size");
+	if (n == 0) return RB_OK;
+	RB_REQUIRE(table && pow2(capacity) && states && index, "bad table or pointers");
+	RB_INIT();
+	cudaStream_t st = S(stream);
+	const unsigned nb = (unsigned)rbf::n_blocks(n);
+	if (rep == RB_REP_2024) {
+		rbf::k_lookup2024<<<nb, rbf::kThreads, 0, st>>>(states, table, capacity, n, index);
+		RB_LAUNCHED("frontier_lookup_2024");
+	} else {
+		RB_REQUIRE(scratch && aligned(scratch, 16) && aligned(states, 4), "6x8x6 lookup needs 16-byte aligned scratch");
+		const rbf::Scratch sc = rbf::scratch_of(scratch, n);
+		rbf::k_pack686<<<(unsigned)((n + 7) / 8), rbf::kThreads, 0, st>>>(states, n, sc.keys);
+		RB_LAUNCHED("frontier_pack_686");
+		rbf::k_lookup_keys<<<nb, rbf::kThreads, 0, st>>>(sc.keys, table, capacity, n, index);
+		RB_LAUNCHED("frontier_lookup_keys");
+	}
+	return RB_OK;
+}
+
+int rb_frontier_expand(int rep, void* table, int64_t capacity, const int8_t* frontier, int64_t n, int32_t* count_dev,
+                       int8_t* next_frontier, int32_t* parent, uint8_t* action, uint8_t* solved, uint8_t* seen, uint8_t* first,
+                       int32_t* index, int32_t* n_new_dev, void* scratch, rb_stream_t stream) {
+	RB_REQUIRE(rep_ok(rep) && n >= 0 && 12 * n < (1ll << 31), "bad rep or size");
+	if (n == 0) {
+		if (n_new_dev) RB_CUDA(cudaMemsetAsync(n_new_dev, 0, sizeof(int32_t), S(stream)));
+		return RB_OK;
+	}
+	RB_REQUIRE(table && pow2(capacity) && aligned(table, 16) && frontier && count_dev && scratch && aligned(scratch, 16), "bad table or pointers");
+	RB_REQUIRE(aligned(next_frontier, 4), "next_frontier must be 4-byte aligned");
+	RB_INIT();
+	const int64_t items = 12 * n;
+	const rbf::Scratch sc = rbf::scratch_of(scratch, items);
+	cudaStream_t st = S(stream);
+	if (rep == RB_REP_2024) {
+		const rbf::FromParent2024 prov{frontier};
+		rbf::k_probe2024<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(prov, table, capacity, items, sc.slot);
+		RB_LAUNCHED("frontier_probe_2024");
+		int rc = frontier_common_tail(table, capacity, items, sc, seen, first, st);
+		if (rc != RB_OK) return rc;
+		rbf::k_assign2024<rbf::FromParent2024, true><<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(
+			prov, table, capacity, items, sc.slot, sc.block_new, count_dev, next_frontier, parent, action, solved);
+		RB_LAUNCHED("frontier_assign_2024");
+	} else {
+		RB_REQUIRE(aligned(frontier, 16) && aligned(next_frontier, 16), "6x8x6 states must be 16-byte aligned");
+		int8_t* children = reinterpret_cast<int8_t*>(sc.keys + items);
+		int32_t* new_items = reinterpret_cast<int32_t*>(children + items * 288);
+		int rc = rb_expand12(RB_REP_686, frontier, children, nullptr, nullptr, n, stream);
+		if (rc != RB_OK) return rc;
+		rbf::k_pack686<<<(unsigned)((items + 7) / 8), rbf::kThreads, 0, st>>>(children, items, sc.keys);
+		RB_LAUNCHED("frontier_pack_686");
+		rbf::k_probe_keys<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(sc.keys, table, capacity, items, sc.slot);
+		RB_LAUNCHED("frontier_probe_keys");
+		rc = frontier_common_tail(table, capacity, items, sc, seen, first, st);
+		if (rc != RB_OK) return rc;
+		rbf::k_assign_ids<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(table, capacity, items, sc.slot, sc.block_new, count_dev, new_items);
+		RB_LAUNCHED("frontier_assign");
+		rbf::k_gather686<<<rb_grid(items, 8, 8), rbf::kThreads, 0, st>>>(children, new_items, sc.block_new, sc.nb, next_frontier, parent,
+		                                                             action, solved);
+		RB_LAUNCHED("frontier_gather_686");
+	}
+	rbf::k_finish<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(table, capacity, items, sc.slot, index);
+	RB_LAUNCHED("frontier_finish");
+	rbf::k_bump<<<1, 1, 0, st>>>(count_dev, sc.block_new, sc.nb, n_new_dev);
+	RB_LAUNCHED("frontier_bump");
+	return RB_OK;
+}
+
+int rb_check_range(int rep, const int8_t* states, int64_t n_states, const uint8_t* faces, const uint8_t* dirs,
+                   int64_t n_actions, int32_t* scratch_dev, rb_stream_t stream) {
+	RB_REQUIRE(rep_ok(rep) && n_states >= 0 && n_actions >= 0 && scratch_dev, "bad argument");
+	const int64_t state_bytes = (states && rep == RB_REP_2024) ? n_states * 20 : 0;
+	if ((!faces || n_actions == 0) && state_bytes == 0) return RB_OK;
+	RB_CUDA(cudaMemsetAsync(scratch_dev, 0, sizeof(int32_t), S(stream)));
+	const int64_t work = state_bytes > n_actions ? state_bytes : n_actions;
+	rbh::k_check_range<<<rb_grid(work, 256 * 8, 8), 256, 0, S(stream)>>>(rep, reinterpret_cast<const uint8_t*>(states), state_bytes,
+	                                                                   faces, dirs, faces ? n_actions : 0, scratch_dev);
+	RB_LAUNCHED("check_range");
+	int32_t flag = 0;
+	RB_CUDA(cudaMemcpyAsync(&flag, scratch_dev, sizeof(flag), cudaMemcpyDeviceToHost, S(stream)));
+	RB_CUDA(cudaStreamSynchronize(S(stream)));
+	if (flag) return rb_fail(RB_ERR_RANGE, "index out of range: face >= 6, direction >= 2, action >= 12 or state value >= 24%s%s");
+	return RB_OK;
+}
+
+// ---- host-buffer entry points ------------------------------------------------------------------------------
+int rbh_scramble(int rep, const uint8_t* actions, int8_t* out, int64_t n, int32_t depth) {
+	RB_REQUIRE(rep_ok(rep) && n >= 0 && depth >= 0, "bad rep or size");
+	if (n == 0) return RB_OK;
+	RB_REQUIRE(out && (actions || depth == 0), "null pointer");
+	RB_INIT();
+	std::lock_guard<std::mutex> lock(rbh::g_stage_mu);
+	const int64_t sb = rep == RB_REP_2024 ? 20 : 288;
+	// chunks of <= 2^20 cubes (a multiple of 256 so every chunk base stays 16-byte aligned), at least 4 chunks
+	int64_t chunk = (n + 3) / 4;
+	chunk = (chunk + 255) / 256 * 256;
+	if (chunk > (1 << 20)) chunk = 1 << 20;
+	int rc = rbh::stage_reserve((size_t)chunk * (depth > 0 ? depth : 1), 0, (size_t)chunk * sb);
+	if (rc != RB_OK) return rc;
+	rbh::Staging& st = rbh::g_stage;
+	int k = 0;
+	for (int64_t base = 0; base < n; base += chunk, k ^= 1) {
+		const int64_t cnt = n - base < chunk ? n - base : chunk;
+		cudaStream_t s = st.stream[k];
+		if (depth > 0)
+			RB_CUDA(cudaMemcpyAsync(st.in[k], actions + base * depth, (size_t)cnt * depth, cudaMemcpyHostToDevice, s));
+		rc = rb_scramble(rep, reinterpret_cast<const uint8_t*>(st.in[k]), depth, 1, nullptr, reinterpret_cast<int8_t*>(st.out[k]), cnt,
+		                 depth, s);
+		if (rc != RB_OK) return rc;
+		RB_CUDA(cudaMemcpyAsync(out + base * sb, st.out[k], (size_t)cnt * sb, cudaMemcpyDeviceToHost, s));
+	}
+	RB_CUDA(cudaStreamSynchronize(st.stream[0]));
+	RB_CUDA(cudaStreamSynchronize(st.stream[1]));
+	return RB_OK;
+}
+
+int rbh_multi_rotate(int rep, const int8_t* states, const uint8_t* faces, const uint8_t* dirs, int8_t* out, int64_t n) {
+	RB_REQUIRE(rep_ok(rep) && n >= 0, "bad rep or size");
+	if (n == 0) return RB_OK;
+	RB_REQUIRE(states && faces && out, "null pointer");
+	RB_INIT();
+	std::lock_guard<std::mutex> lock(rbh::g_stage_mu);
+	const int64_t sb = rep == RB_REP_2024 ? 20 : 288;
+	int64_t chunk = (n + 3) / 4;
+	chunk = (chunk + 255) / 256 * 256;
+	if (chunk > (1 << 22)) chunk = 1 << 22;
+	int rc = rbh::stage_reserve((size_t)chunk * sb, (size_t)chunk * 2, (size_t)chunk * sb);
+	if (rc != RB_OK) return rc;
+	rbh::Staging& st = rbh::g_stage;
+	int k = 0;
+	for (int64_t base = 0; base < n; base += chunk, k ^= 1) {
+		const int64_t cnt = n - base < chunk ? n - base : chunk;
+		cudaStream_t s = st.stream[k];
+		uint8_t* f_dev = reinterpret_cast<uint8_t*>(st.in2[k]);
+		uint8_t* d_dev = dirs ? f_dev + chunk : nullptr;
+		RB_CUDA(cudaMemcpyAsync(st.in[k], states + base * sb, (size_t)cnt * sb, cudaMemcpyHostToDevice, s));
+		RB_CUDA(cudaMemcpyAsync(f_dev, faces + base, (size_t)cnt, cudaMemcpyHostToDevice, s));
+		if (dirs) RB_CUDA(cudaMemcpyAsync(d_dev, dirs + base, (size_t)cnt, cudaMemcpyHostToDevice, s));
+		rc = rb_multi_rotate(rep, reinterpret_cast<const int8_t*>(st.in[k]), f_dev, d_dev, reinterpret_cast<int8_t*>(st.out[k]), cnt, s);
+		if (rc != RB_OK) return rc;
+		RB_CUDA(cudaMemcpyAsync(out + base * sb, st.out[k], (size_t)cnt * sb, cudaMemcpyDeviceToHost, s));
+	}
+	RB_CUDA(cudaStreamSynchronize(st.stream[0]));
+	RB_CUDA(cudaStreamSynchronize(st.stream[1]));
+	return RB_OK;
+}
+
+int rbh_release(void) {
+	std::lock_guard<std::mutex> lock(rbh::g_stage_mu);
+	return rbh::stage_release();
+}
+
+}  // extern "C"

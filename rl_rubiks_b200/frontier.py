@@ -1,0 +1,320 @@
+"""
+Search frontier on the device: the seen-set, child expansion and dedup that `BFS`, `AStar` and `MCTS` do with a
+Python dict keyed on `state.tostring()` (reference: librubiks/solving/agents.py:96-123, 254-331, 511-544, 597-611).
+
+`StateHashSet` is an open-addressing hash set on the packed state in caller-owned (torch) device memory with the
+reference's index semantics: states are numbered 1, 2, ... in insertion order, a batch is numbered in batch order,
+in-batch duplicates resolve to their first occurrence (agents.py:286-306).  `BFS` and `AStar` mirror the reference
+agents' interface (`search(state, time_limit, max_states) -> bool`, `action_queue`, `len(agent)`).
+"""
+from __future__ import annotations
+
+import heapq
+from collections import deque
+from time import perf_counter
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import cube
+
+
+def _pow2_at_least(x: int) -> int:
+	return 1 << max(4, int(x - 1).bit_length())
+
+
+class StateHashSet:
+	def __init__(self, capacity: int = 1 << 16, is2024: bool | None = None):
+		N.require_cuda()
+		self.is2024 = cube.get_is2024() if is2024 is None else is2024
+		self.rep = N.REP_2024 if self.is2024 else N.REP_686
+		self.shape = (20,) if self.is2024 else (6, 8, 6)
+		self.dev = torch.device("cuda", torch.cuda.current_device())
+		self.capacity = _pow2_at_least(capacity)
+		self.table = torch.empty(N.lib.rb_hashset_bytes(self.capacity), dtype=torch.uint8, device=self.dev)
+		self.count = torch.zeros(1, dtype=torch.int32, device=self.dev)
+		self.n_new = torch.zeros(1, dtype=torch.int32, device=self.dev)
+		self._upper = 0                      # host-side upper bound of the set size (no sync needed)
+		self._scratch = None
+		self.clear()
+
+	def clear(self):
+		N.check(N.lib.rb_hashset_clear(N.ptr(self.table), self.capacity, N.stream_handle()))
+		self.count.zero_()
+		self._upper = 0
+
+	def __len__(self) -> int:
+		n = int(self.count.item())
+		self._upper = n
+		return n
+
+	def _reserve(self, incoming: int):
+		"""Keeps the load factor <= 1/2 using the host-side upper bound (exact size read back only when needed)."""
+		if 2 * (self._upper + incoming) <= self.capacity:
+			return
+		len(self)
+		if 2 * (self._upper + incoming) <= self.capacity:
+			return
+		new_cap = _pow2_at_least(4 * (self._upper + incoming))
+		new_table = torch.empty(N.lib.rb_hashset_bytes(new_cap), dtype=torch.uint8, device=self.dev)
+		N.check(N.lib.rb_hashset_rehash(N.ptr(self.table), self.capacity, N.ptr(new_table), new_cap, N.stream_handle()))
+		self.table, self.capacity = new_table, new_cap
+
+	def _scratch_for(self, nbytes: int) -> torch.Tensor:
+		if self._scratch is None or self._scratch.numel() < nbytes:
+			self._scratch = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=self.dev)
+		return self._scratch
+
+	def _states(self, states):
+		if isinstance(states, torch.Tensor):
+			t, was_np = states.to(device=self.dev, dtype=torch.int8), False
+		else:
+			t, was_np = torch.from_numpy(np.ascontiguousarray(states, dtype=np.int8)).to(self.dev), True
+		if t.dim() == len(self.shape):
+			t = t.unsqueeze(0)
+		if tuple(t.shape[1:]) != self.shape:
+			raise IndexError(f"states of shape {tuple(t.shape)} do not match {self.shape}")
+		return t.contiguous(), was_np
+
+	def insert_unique(self, states):
+		"""-> (seen bool (n,), first bool (n,), index int32 (n,)) with the semantics of agents.py:286-306."""
+		s, was_np = self._states(states)
+		n = s.shape[0]
+		self._reserve(n)
+		seen = torch.empty(n, dtype=torch.uint8, device=self.dev)
+		first = torch.empty(n, dtype=torch.uint8, device=self.dev)
+		index = torch.empty(n, dtype=torch.int32, device=self.dev)
+		scratch = self._scratch_for(N.lib.rb_hashset_scratch_bytes(n))
+		N.check(N.lib.rb_hashset_insert_unique(self.rep, N.ptr(self.table), self.capacity, N.ptr(s), n, N.ptr(self.count), N.ptr(seen),
+											   N.ptr(first), N.ptr(index), N.ptr(scratch), N.stream_handle()))
+		self._upper += n
+		out = (seen.bool(), first.bool(), index)
+		return tuple(x.cpu().numpy() for x in out) if was_np else out
+
+	def lookup(self, states):
+		"""Index of every state, 0 when absent (agents.py:606-607)."""
+		s, was_np = self._states(states)
+		n = s.shape[0]
+		index = torch.empty(n, dtype=torch.int32, device=self.dev)
+		scratch = self._scratch_for(N.lib.rb_hashset_scratch_bytes(n))
+		N.check(N.lib.rb_hashset_lookup(self.rep, N.ptr(self.table), self.capacity, N.ptr(s), n, N.ptr(index), N.ptr(scratch), N.stream_handle()))
+		return index.cpu().numpy() if was_np else index
+
+	def expand(self, frontier: torch.Tensor, flags: bool = False, parents: bool = True, solved: bool = True, index: bool = False):
+		"""One frontier step: 12 children of every frontier state, dedup against the set and within the batch, new states
+		compacted in batch order.  Returns a dict of device tensors sized for the worst case (12 n rows); the first
+		`n_new` rows are valid.  `n_new` itself stays on the device (`out['n_new']`) until the caller reads it."""
+		f, _ = self._states(frontier)
+		n = f.shape[0]
+		m = 12 * n
+		self._reserve(m)
+		out = {"next": torch.empty(m, *self.shape, dtype=torch.int8, device=self.dev)}
+		out["parent"] = torch.empty(m, dtype=torch.int32, device=self.dev) if parents else None
+		out["action"] = torch.empty(m, dtype=torch.uint8, device=self.dev) if parents else None
+		out["solved"] = torch.empty(m, dtype=torch.uint8, device=self.dev) if solved else None
+		out["seen"] = torch.empty(m, dtype=torch.uint8, device=self.dev) if flags else None
+		out["first"] = torch.empty(m, dtype=torch.uint8, device=self.dev) if flags else None
+		out["index"] = torch.empty(m, dtype=torch.int32, device=self.dev) if index else None
+		scratch = self._scratch_for(N.lib.rb_frontier_scratch_bytes(self.rep, n))
+		N.check(N.lib.rb_frontier_expand(self.rep, N.ptr(self.table), self.capacity, N.ptr(f), n, N.ptr(self.count), N.ptr(out["next"]),
+										 N.ptr(out["parent"]), N.ptr(out["action"]), N.ptr(out["solved"]), N.ptr(out["seen"]),
+										 N.ptr(out["first"]), N.ptr(out["index"]), N.ptr(self.n_new), N.ptr(scratch), N.stream_handle()))
+		self._upper += m
+		out["n_new"] = self.n_new
+		return out
+
+
+def bfs_layers(max_depth: int, start=None, is2024: bool | None = None, capacity: int | None = None):
+	"""Layer-synchronous BFS closure from `start` (default solved): per-depth counts of newly discovered states
+	(1, 12, 114, 1068, ... for the 20x24 cube) and the StateHashSet.  Everything but one int per layer stays on the device."""
+	is2024 = cube.get_is2024() if is2024 is None else is2024
+	hs = StateHashSet(capacity or (1 << 16), is2024)
+	if start is None:
+		start = cube._solved[hs.rep]
+	frontier, _ = hs._states(start)
+	hs.insert_unique(frontier)
+	counts = [1]
+	for _ in range(max_depth):
+		out = hs.expand(frontier, parents=False, solved=False)
+		n_new = int(out["n_new"].item())
+		frontier = out["next"][:n_new]
+		counts.append(n_new)
+	return counts, hs
+
+
+class Agent:
+	"""Interface of the reference agents (agents.py:14-64)."""
+
+	def __init__(self):
+		self.action_queue = deque()
+		self._explored_states = 0
+
+	def reset(self, time_limit, max_states):
+		self._explored_states = 0
+		self.action_queue = deque()
+		if hasattr(self, "net"):
+			self.net.eval()
+		assert time_limit or max_states
+		return time_limit or 1e10, max_states or int(1e10)
+
+	def __len__(self):
+		return self._explored_states
+
+
+class BFS(Agent):
+	"""Breadth-first search (agents.py:92-129), one kernel sequence per layer instead of one dict probe per child.
+	Visits parents in discovery order and children in action order, so the first solved child found, the recorded
+	(parent, action) links and `len(agent)` are those of the reference's FIFO loop."""
+
+	def __init__(self, is2024: bool | None = None):
+		super().__init__()
+		self.is2024 = is2024
+
+	def search(self, state, time_limit: float = None, max_states: int = None) -> bool:
+		time_limit, max_states = self.reset(time_limit, max_states)
+		t0 = perf_counter()
+		is2024 = cube.get_is2024() if self.is2024 is None else self.is2024
+		hs = StateHashSet(1 << 16, is2024)
+		frontier, _ = hs._states(state)
+		if bool((frontier[0].cpu().numpy() == cube._solved[hs.rep]).all()):
+			return True
+		hs.insert_unique(frontier)
+		total = 1
+		layers = []                                   # per layer: (parent position in previous layer, action)
+		while perf_counter() - t0 < time_limit and total < max_states and frontier.shape[0]:
+			out = hs.expand(frontier, flags=True)
+			n_new = int(out["n_new"].item())
+			solved = out["solved"][:n_new]
+			hit = torch.nonzero(solved)
+			layers.append((out["parent"][:n_new], out["action"][:n_new]))
+			if hit.numel():
+				k = int(hit[0].item())                # first solved new child in batch (= FIFO) order
+				# the reference stops before recording the solved child: the dict holds the states discovered before it
+				self._explored_states = total + k
+				pos = k
+				for parent, action in reversed(layers):
+					self.action_queue.appendleft(int(action[pos].item()))
+					pos = int(parent[pos].item())
+				return True
+			total += n_new
+			self._explored_states = total
+			frontier = out["next"][:n_new]
+		return False
+
+	def __str__(self):
+		return "Breadth-first search"
+
+
+class AStar(Agent):
+	"""Batched weighted A* (agents.py:171-413).  Device: child expansion, seen-set dedup with batch-order index
+	assignment, compaction of the new states, one-hot, value net, solved test.  Host (as in the reference; the device
+	open list is SURVEY 8f row N2): the heapq open list of (cost, index) and the G / parent relaxation."""
+
+	_stack_expand = 1000
+
+	def __init__(self, net, lambda_: float, expansions: int, is2024: bool | None = None):
+		super().__init__()
+		self.net, self.lambda_, self.expansions, self.is2024 = net, lambda_, expansions, is2024
+
+	def reset(self, time_limit, max_states):
+		time_limit, max_states = super().reset(time_limit, max_states)
+		is2024 = cube.get_is2024() if self.is2024 is None else self.is2024
+		self.hs = StateHashSet(1 << 16, is2024)
+		self.open_queue = []
+		self.states = torch.empty(self._stack_expand, *self.hs.shape, dtype=torch.int8, device=self.hs.dev)
+		self.parents = np.empty(self._stack_expand, dtype=int)
+		self.parent_actions = np.zeros(self._stack_expand, dtype=int)
+		self.G = np.empty(self._stack_expand)
+		self.n_states = 0
+		return time_limit, max_states
+
+	def increase_stack_size(self):
+		self.states = torch.cat([self.states, torch.empty_like(self.states)])
+		self.parents = np.concatenate([self.parents, np.zeros_like(self.parents)])
+		self.parent_actions = np.concatenate([self.parent_actions, np.zeros_like(self.parent_actions)])
+		self.G = np.concatenate([self.G, np.empty_like(self.G)])
+
+	def __len__(self):
+		return self.n_states
+
+	@torch.no_grad()
+	def search(self, state, time_limit: float = None, max_states: int = None) -> bool:
+		t0 = perf_counter()
+		time_limit, max_states = self.reset(time_limit, max_states)
+		root, _ = self.hs._states(state)
+		if bool((root[0].cpu().numpy() == cube._solved[self.hs.rep]).all()):
+			return True
+		self.hs.insert_unique(root)
+		self.states[1], self.G[1], self.n_states = root[0], 0, 1
+		heapq.heappush(self.open_queue, (0, 1))
+		while perf_counter() - t0 < time_limit and len(self) + self.expansions * 12 <= max_states:
+			n_remove = min(len(self.open_queue), self.expansions)
+			expand_idcs = np.array([heapq.heappop(self.open_queue)[1] for _ in range(n_remove)], dtype=int)
+			if self.expand_batch(expand_idcs):
+				i = self.solved_index
+				while i != 1:
+					self.action_queue.appendleft(int(self.parent_actions[i]))
+					i = int(self.parents[i])
+				return True
+		return False
+
+	def expand_batch(self, expand_idcs: np.ndarray) -> bool:
+		"""agents.py:254-331."""
+		expand_size = len(expand_idcs)
+		while len(self) + expand_size * 12 >= len(self.states):
+			self.increase_stack_size()
+		idcs_dev = torch.from_numpy(expand_idcs).to(self.hs.dev)
+		out = self.hs.expand(self.states[idcs_dev], flags=True, index=True)
+		n_new = int(out["n_new"].item())
+		base = self.n_states
+		new_states = out["next"][:n_new]
+		self.states[base + 1:base + 1 + n_new] = new_states
+		self.n_states = base + n_new
+		new_idcs = base + np.arange(n_new) + 1
+		parent_pos = out["parent"][:n_new].cpu().numpy()
+		new_parent_idcs = expand_idcs[parent_pos]
+		self.G[new_idcs] = self.G[new_parent_idcs] + 1
+		self.parent_actions[new_idcs] = out["action"][:n_new].cpu().numpy()
+		self.parents[new_idcs] = new_parent_idcs
+		if n_new:
+			costs = self.cost(new_states, new_idcs)
+			for c, i in zip(costs, new_idcs):
+				heapq.heappush(self.open_queue, (c, int(i)))
+			solved = out["solved"][:n_new]
+			if bool(solved.any().item()):
+				self.solved_index = int(new_idcs[int(torch.nonzero(solved)[0].item())])
+				return True
+		seen = out["seen"].bool().cpu().numpy()
+		first = out["first"].bool().cpu().numpy()
+		index = out["index"].cpu().numpy().astype(int)
+		old = first & seen
+		parent_idcs = np.repeat(expand_idcs, 12)
+		actions_taken = np.tile(np.arange(12), expand_size)
+		self.relax_seen_states(index[old], parent_idcs[old], actions_taken[old])
+		return False
+
+	def relax_seen_states(self, state_idcs, parent_idcs, actions_taken):
+		"""agents.py:333-367."""
+		new_ways = self.G[parent_idcs] + 1 < self.G[state_idcs]
+		nw_states, nw_parents = state_idcs[new_ways], parent_idcs[new_ways]
+		self.G[nw_states] = self.G[nw_parents] + 1
+		self.parent_actions[nw_states] = actions_taken[new_ways]
+		self.parents[nw_states] = nw_parents
+		shortcuts = self.G[state_idcs] + 1 < self.G[parent_idcs]
+		sc_states, sc_parents = state_idcs[shortcuts], parent_idcs[shortcuts]
+		self.G[sc_parents] = self.G[sc_states] + 1
+		self.parent_actions[sc_parents] = cube.rev_actions(actions_taken[shortcuts])
+		self.parents[sc_parents] = sc_states
+
+	@torch.no_grad()
+	def cost(self, states: torch.Tensor, indeces: np.ndarray) -> np.ndarray:
+		"""agents.py:369-383: lambda * G + H with H = -value net; one-hot born on the device."""
+		oh = torch.empty(states.shape[0], 480 if self.hs.is2024 else 288, dtype=torch.float32, device=self.hs.dev)
+		N.check(N.lib.rb_as_oh(self.hs.rep, N.ptr(states.contiguous()), N.ptr(oh), states.shape[0], N.stream_handle()))
+		H = -self.net(oh, value=True, policy=False)
+		H = H.cpu().squeeze(-1).detach().numpy() if H.dim() > 1 else H.cpu().detach().numpy()
+		return self.lambda_ * self.G[indeces] + H
+
+	def __str__(self):
+		return f'AStar (lambda={self.lambda_}, N={self.expansions})'

@@ -1,0 +1,161 @@
+"""GPU parity tests for the search frontier: hash-set dedup with the reference's batch-order
+index semantics, BFS layer counts (known answers), the BFS and A* agents against traces recorded from the reference."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cube_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+REPS = [pytest.param(True, id="2024"), pytest.param(False, id="686")]
+
+
+@pytest.fixture(autouse=True)
+def _repr_guard():
+	from rl_rubiks_b200 import cube
+	cube.set_is2024(True)
+	yield
+	cube.set_is2024(True)
+
+
+def _states(n, is2024, seed, depth):
+	g = np.random.RandomState(seed)
+	return O.scramble_many(g.randint(0, 6, (n, depth)), g.randint(0, 2, (n, depth)), is2024)
+
+
+@pytest.mark.parametrize("is2024", REPS)
+def test_insert_unique_matches_dict_semantics(is2024):
+	"""agents.py:286-306: seen / first-occurrence flags and batch-order indices, with heavy in-batch duplication, across
+	several batches and through table growth."""
+	from rl_rubiks_b200.frontier import StateHashSet
+	hs = StateHashSet(16, is2024)
+	ref = O.SeenSet()
+	for b, (n, depth) in enumerate(((1, 0), (500, 2), (3000, 3), (257, 1), (5000, 4))):
+		s = _states(n, is2024, seed=b, depth=depth) if depth else O.solved(is2024)[None]
+		seen, first, idx = hs.insert_unique(s)
+		w_seen, w_first, w_idx = ref.insert_unique(s)
+		assert (seen == w_seen).all() and (first == w_first).all() and (idx == w_idx).all()
+		assert len(hs) == len(ref)
+	probe = np.concatenate([_states(100, is2024, seed=99, depth=6), _states(100, is2024, seed=1, depth=2)])
+	assert (hs.lookup(probe) == ref.lookup(probe)).all()
+
+
+@pytest.mark.parametrize("is2024,depth", [pytest.param(True, 6, id="2024"), pytest.param(False, 4, id="686")])
+def test_bfs_layer_counts_known_answers(is2024, depth):
+	"""SURVEY 8c KAT (i): 1, 12, 114, 1068, 10011, 93840, 878880 new states per depth (computed with the reference)."""
+	from rl_rubiks_b200.frontier import bfs_layers
+	counts, hs = bfs_layers(depth, is2024=is2024)
+	assert counts == [1, 12, 114, 1068, 10011, 93840, 878880][:depth + 1]
+	assert len(hs) == sum(counts)
+
+
+def test_frontier_expand_vs_oracle_step_by_step():
+	from rl_rubiks_b200.frontier import StateHashSet
+	for is2024 in (True, False):
+		hs, ref = StateHashSet(1 << 10, is2024), O.SeenSet()
+		frontier = _states(40, is2024, seed=7, depth=3)
+		_, first, _ = ref.insert_unique(frontier)
+		hs.insert_unique(frontier)
+		frontier = frontier[first]
+		for _ in range(2):
+			out = hs.expand(torch.from_numpy(frontier).cuda(), flags=True, index=True)
+			children = O.expand12(frontier, is2024)
+			seen, first, idx = ref.insert_unique(children)
+			new = first & ~seen
+			n_new = int(out["n_new"].item())
+			assert n_new == new.sum()
+			assert (out["next"][:n_new].cpu().numpy() == children[new]).all()
+			assert (out["parent"][:n_new].cpu().numpy() == np.repeat(np.arange(len(frontier)), 12)[new]).all()
+			assert (out["action"][:n_new].cpu().numpy() == np.tile(np.arange(12), len(frontier))[new]).all()
+			assert (out["solved"][:n_new].cpu().numpy().astype(bool) == O.multi_is_solved(children[new], is2024)).all()
+			assert (out["seen"].cpu().numpy().astype(bool) == seen).all() and (out["first"].cpu().numpy().astype(bool) == first).all()
+			assert (out["index"].cpu().numpy() == idx).all()
+			frontier = children[new]
+
+
+def test_bfs_agent_matches_reference(golden):
+	"""BFS.search (agents.py:96-123): found flag, states explored and action queue recorded from the reference."""
+	from rl_rubiks_b200 import cube
+	from rl_rubiks_b200.frontier import BFS
+	g = golden("search")
+	agent = BFS()
+	assert agent.search(g["bfs_start"], None, 10 ** 6) == bool(g["bfs_found"])
+	assert len(agent) == int(g["bfs_len"])
+	assert list(agent.action_queue) == g["bfs_queue"].tolist()
+	s = g["bfs_start"]
+	for a in agent.action_queue:
+		s = cube.rotate(s, *cube.action_space[a])
+	assert cube.is_solved(s)
+	assert BFS().search(cube.get_solved(), None, 10) is True
+
+
+class _FakeNet(torch.nn.Module):
+	def __init__(self, w, quant=4.0):
+		super().__init__()
+		self.w, self.quant = torch.from_numpy(np.asarray(w, dtype=np.float32)).cuda(), quant
+
+	def forward(self, x, policy=True, value=True):
+		return torch.floor((x @ self.w) / self.quant).unsqueeze(1)
+
+
+@pytest.mark.parametrize("is2024", REPS)
+def test_astar_expand_batch_trace_matches_reference(golden, is2024):
+	"""AStar.expand_batch (agents.py:254-331) step by step: popped batches, set sizes, stored states, G, parents and
+	parent actions equal the trace recorded from the reference with a tie-heavy integer net."""
+	import heapq
+	from rl_rubiks_b200 import cube
+	from rl_rubiks_b200.frontier import AStar
+	cube.set_is2024(is2024)
+	tag = "2024" if is2024 else "686"
+	g = golden("search")
+	a = AStar(_FakeNet(g[f"astar_w_{tag}"]), lambda_=0.16, expansions=7)
+	a.reset(None, 10 ** 6)
+	root, _ = a.hs._states(g[f"astar_start_{tag}"])
+	a.hs.insert_unique(root)
+	a.states[1], a.G[1], a.n_states = root[0], 0, 1
+	a.open_queue = [(0, 1)]
+	won = False
+	for step, want in enumerate(g[f"astar_batches_{tag}"]):
+		n = min(len(a.open_queue), a.expansions)
+		idcs = np.array([heapq.heappop(a.open_queue)[1] for _ in range(n)], dtype=int)
+		assert idcs.tolist() == want[want >= 0].tolist()
+		won = a.expand_batch(idcs)
+		assert len(a) == g[f"astar_lens_{tag}"][step] == len(a.hs)
+		if won:
+			break
+	assert won == bool(g[f"astar_won_{tag}"])
+	L = len(a)
+	assert (a.states[1:L + 1].cpu().numpy() == g[f"astar_states_{tag}"]).all()
+	assert (a.G[1:L + 1] == g[f"astar_G_{tag}"]).all()
+	assert (a.parents[2:L + 1] == g[f"astar_parents_{tag}"]).all()
+	assert (a.parent_actions[2:L + 1] == g[f"astar_pact_{tag}"]).all()
+	assert np.array_equal(np.array(sorted(a.open_queue)), g[f"astar_open_{tag}"])
+
+
+def test_astar_full_search_matches_reference(golden):
+	from rl_rubiks_b200 import cube
+	from rl_rubiks_b200.frontier import AStar
+	g = golden("search")
+	a = AStar(_FakeNet(np.zeros(480)), lambda_=1.0, expansions=5)
+	assert a.search(g["astar_full_start"], None, 20000) == bool(g["astar_full_ok"])
+	assert len(a) == int(g["astar_full_len"]) and list(a.action_queue) == g["astar_full_queue"].tolist()
+	s = g["astar_full_start"]
+	for act in a.action_queue:
+		s = cube.rotate(s, *cube.action_space[act])
+	assert cube.is_solved(s)
+	# reference tests/test_agents.py:122-134: after a search the 12 children of the root have G == 1 and parent == 1
+	assert (a.G[2:14] == 1).all() and (a.parents[2:14] == 1).all()
+
+
+def test_mcts_style_lookup(golden):
+	"""MCTS bookkeeping (agents.py:511-544, 597-611): contiguous indices in discovery order, neighbour lookups."""
+	from rl_rubiks_b200.frontier import StateHashSet
+	g = golden("search")
+	states, nb, leaves = g["mcts_states"], g["mcts_neighbors"], g["mcts_leaves"]
+	hs = StateHashSet(1 << 12, True)
+	_, first, idx = hs.insert_unique(states)
+	assert first.all() and idx.tolist() == list(range(1, len(states) + 1))
+	inner = np.where(~leaves[1:])[0] + 1
+	ch_idx = hs.lookup(O.expand12(states[inner - 1], True)).reshape(-1, 12)
+	assert (ch_idx == nb[inner]).all()
