@@ -2,6 +2,7 @@
 #include "rb_common.cuh"
 #include "rb_tables.cuh"
 #include "rb_cube2024.cuh"
+#include "rb_scramble_macro.cuh"
 #include "rb_cube686.cuh"
 #include "rb_adi.cuh"
 #include "rb_frontier.cuh"
@@ -36,6 +37,13 @@ int rb_get_lut2024(uint8_t* lut) {
 int rb_get_perm686(uint8_t* perm) {
 	RB_REQUIRE(perm, "null output");
 	memcpy(perm, rbt::host().perm686, sizeof(rbt::host().perm686));
+	return RB_OK;
+}
+int rb_get_macro_table(uint32_t* rows) {
+	RB_REQUIRE(rows, "null output");
+	const rbs::Host& h = rbs::host();
+	if (!h.ok) return rb_fail(RB_ERR_BAD_ARG, "macro-move table: corner twist is not additive for these move tables%s%s");
+	memcpy(rows, h.rows, sizeof(uint32_t) * rbs::kRows * rbs::kRowWords);
 	return RB_OK;
 }
 int rb_get_solved(int rep, int8_t* state) {
@@ -129,6 +137,8 @@ int rb_scramble(int rep, const uint8_t* actions, int64_t stride_cube, int64_t st
 	RB_REQUIRE(out && (actions || depth == 0), "null pointer");
 	RB_INIT();
 	if (rep == RB_REP_2024) {
+		if (!start && depth > 0 && stride_move == 1 && stride_cube == depth && aligned(actions, 16) && rbs::tile_for(n, depth) > 0)
+			return rbs::launch(actions, out, n, depth, S(stream));      // slot-major macro-move kernel (cube-major actions)
 		rb2024::k_scramble<<<rb_grid(n, rb2024::kThreads, 8), rb2024::kThreads, 0, S(stream)>>>(
 			actions, stride_cube, stride_move, start, out, n, depth);
 		RB_LAUNCHED("scramble_2024");
