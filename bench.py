@@ -249,9 +249,9 @@ def run_gpu(args):
 		"config": {"workload": WORKLOAD, "cubes_per_gpu": n, "depth": depth, "actions": "host-supplied uint8 [n][100], resident in HBM",
 				   "l2": "inputs (1.68 GB actions) larger than the 126 MB L2, no reuse between steps", "parity_subsample_ok": parity_ok},
 		"roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-					 "peak_source": peak_src, "kernel": "rb2024::k_scramble", "kernel_ms": kernel_ms,
+					 "peak_source": peak_src, "kernel": "rbs::k_scramble_macro<3, aligned, double-buffered>", "kernel_ms": kernel_ms,
 					 "algorithmic_bytes_per_launch": BYTES_PER_CUBE * n,
-					 "note": "multi-move scramble is bound by shared-memory LUT lookups (20 per move), not HBM: see DESIGN.md"},
+					 "note": "multi-move scramble is bound by shared-memory table fetches + PRMT issue, not HBM: see DESIGN.md"},
 		"cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
 						 "sample": f"{cores} processes x {1 << 14} cubes x {depth} moves, numpy oracle port, {cpu_dt:.1f} s"},
 		"e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * depth, "d2h_bytes_per_step": n * 20,
