@@ -61,8 +61,8 @@ int64_t     rb_launch_count(void);
 int rb_get_delta_maps(int8_t* delta);
 int rb_get_lut2024(uint8_t* lut);
 int rb_get_perm686(uint8_t* perm);
-/* The fused 3-move table of the fast scramble kernel (csrc/rb_scramble_macro.cuh): uint32[13*13*13][6], row index
- * a0 + 13 a1 + 169 a2 (action 12 = identity), derived from the 20x24 LUT.  For inspection / CPU emulation tests. */
+/* The fused 2-move table of the fast scramble kernel (csrc/rb_scramble_macro.cuh): uint32[13*13][5], row index
+ * a0 + 13 a1 (action 12 = identity), derived from the 20x24 LUT.  For inspection / CPU emulation tests. */
 int rb_get_macro_table(uint32_t* rows);
 /* get_solved (cube.py:58-83): writes int8[20] or int8[288] to a HOST buffer. */
 int rb_get_solved(int rep, int8_t* state);

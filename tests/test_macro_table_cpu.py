@@ -1,5 +1,5 @@
 """CPU emulation of the slot-major macro-move scramble (rl_rubiks_b200/csrc/rb_scramble_macro.cuh) from the table the
-library exports: the same row decoding, PRMT gathers, twist accumulation and final cubie-major rebuild as the kernel, in
+library exports: the same row decoding, PRMT gathers, 5-bit twist accumulation with periodic folding and final cubie-major rebuild as the kernel, in
 numpy, against the oracle.  Validates the table and the algorithm without a GPU; the kernel itself is checked by the
 `-m gpu` scramble tests."""
 import numpy as np
@@ -10,7 +10,7 @@ from oracle import cube_oracle as O
 
 def _table():
 	from rl_rubiks_b200 import _native as N
-	rows = np.empty((13 ** 3, 6), dtype=np.uint32)
+	rows = np.empty((13 ** 2, 5), dtype=np.uint32)
 	N.check(N.lib.rb_get_macro_table(rows.ctypes.data))
 	return rows
 
@@ -22,39 +22,51 @@ def _prmt(a, b, sel):
 	return np.take_along_axis(src, idx, axis=1)
 
 
+def _bytes_of(word):
+	return np.stack([(word >> (8 * i)) & 0xff for i in range(4)], axis=1).astype(np.uint8)
+
+
+def _fold(c):
+	"""fold_twists(): keeps the 5-bit twist accumulators <= 10 without changing them mod 3."""
+	t = (c & 31).astype(np.int64)
+	assert (t <= 31).all()
+	t = (t & 3) + ((t >> 2) & 7)
+	assert (t <= 10).all()
+	return ((c & 0xe0) | t.astype(np.uint8)).astype(np.uint8)
+
+
 def _emulate(actions, rows):
 	n, depth = actions.shape
-	pad = (-depth) % 3
+	pad = (-depth) % 2
 	a = np.concatenate([actions, np.full((n, pad), 12, np.uint8)], axis=1).astype(np.int64)
-	C = np.tile(np.arange(8, dtype=np.uint8), (n, 1))
-	W = np.zeros((n, 8), dtype=np.int64)
-	E = np.tile(np.arange(12, dtype=np.uint8), (n, 1))
-	for m in range(0, depth + pad, 3):
-		r = rows[a[:, m] + 13 * a[:, m + 1] + 169 * a[:, m + 2]]
-		sc, tw, fl = r[:, 0], r[:, 4], r[:, 5]
-		C0, C1 = _prmt(C[:, :4], C[:, 4:], sc), _prmt(C[:, :4], C[:, 4:], sc >> 16)
-		Wb = W.astype(np.uint8)
-		assert (W < 256).all()
-		W0, W1 = _prmt(Wb[:, :4], Wb[:, 4:], sc).astype(np.int64), _prmt(Wb[:, :4], Wb[:, 4:], sc >> 16).astype(np.int64)
-		W0 += np.stack([(tw >> (8 * i)) & 15 for i in range(4)], axis=1)
-		W1 += np.stack([(tw >> (8 * i + 4)) & 15 for i in range(4)], axis=1)
-		C, W = np.concatenate([C0, C1], 1), np.concatenate([W0, W1], 1)
+	C = np.tile((np.arange(8, dtype=np.uint8) << 5).astype(np.uint8), (n, 1))      # twist accumulator | id << 5
+	E = np.tile(np.arange(12, dtype=np.uint8), (n, 1))                             # id | flip << 4
+	steps = 0
+	for m in range(0, depth + pad, 2):
+		r = rows[a[:, m] + 13 * a[:, m + 1]]
+		sc, tf = r[:, 0], r[:, 4]
+		c0 = _prmt(C[:, :4], C[:, 4:], sc).astype(np.int64) + _bytes_of(tf & 0x03030303)
+		c1 = _prmt(C[:, :4], C[:, 4:], sc >> 16).astype(np.int64) + _bytes_of((tf >> 2) & 0x03030303)
+		assert ((c0 & 31) >= (_bytes_of(tf & 0x03030303))).all() and (c0 < 256).all() and (c1 < 256).all()   # no carry into the id bits
+		C = np.concatenate([c0, c1], 1).astype(np.uint8)
 		Es = []
 		for d in range(3):
 			s = r[:, 1 + d]
 			x = _prmt(E[:, :4], E[:, 4:8], s)
 			e = _prmt(x, E[:, 8:], s >> 16)
-			e = e ^ (np.stack([(fl >> (8 * i + 4 + d)) & 1 for i in range(4)], axis=1).astype(np.uint8) << 4)
-			Es.append(e)
+			Es.append(e ^ _bytes_of(tf & (0x10101010 << d)))                    # partial flip bit 4 + d
 		E = np.concatenate(Es, 1)
+		steps += 1
+		if steps == 10:                                                            # kReduceEvery
+			steps, C = 0, _fold(C)
 	out = np.zeros((n, 20), dtype=np.int8)
 	rows_i = np.arange(n)
 	for q in range(8):
-		t = W[:, q] % 3
+		t = (C[:, q] & 31).astype(np.int64) % 3
 		ori = np.where(np.isin(q, (0, 2, 5, 7)), (3 - t) % 3, t)
-		out[rows_i, C[:, q] & 7] = 3 * q + ori
+		out[rows_i, C[:, q] >> 5] = 3 * q + ori
 	for q in range(12):
-		out[rows_i, 8 + (E[:, q] & 15)] = 2 * q + ((E[:, q] >> 4) & 1)
+		out[rows_i, 8 + (E[:, q] & 15)] = 2 * q + (((E[:, q] >> 4) ^ (E[:, q] >> 5) ^ (E[:, q] >> 6)) & 1)
 	return out
 
 
@@ -72,5 +84,6 @@ def test_macro_table_rows_are_permutations():
 	sc = rows[:, 0]
 	src = np.stack([(sc >> (4 * i)) & 15 for i in range(8)], axis=1)
 	assert (np.sort(src, axis=1) == np.arange(8)).all()
-	ident = rows[12 + 13 * 12 + 169 * 12]
-	assert ident[0] == 0x76543210 and ident[4] == 0 and ident[5] == 0
+	ident = rows[12 + 13 * 12]
+	assert ident[0] == 0x76543210 and ident[4] == 0
+	assert ((rows[:, 4] & 0x80808080) == 0).all()                                   # bit 7 of every twist|flip byte unused
