@@ -51,6 +51,9 @@ static inline int rb_grid(int64_t work_items, int per_block, int blocks_per_sm) 
 // g_lut2024[(a*2 + kind)*32 + s] = new value of a cubie with value s under action a (rows padded 24 -> 32
 // with the identity so that a masked out-of-range value stays in bounds).
 __device__ __align__(16) uint8_t g_lut2024[12 * 2 * 32];
+// The same LUT in constant memory, as words: c_lut2024[a*16 + kind*8 + k] = entries 4k..4k+3.  Kernels that apply the
+// SAME action in every lane (12-neighbour expansion) read rows as constant-bank operands: no shared-memory traffic.
+__constant__ uint32_t c_lut2024[12 * 16];
 // g_perm686[a*48 + slot] = source sticker slot.
 __device__ __align__(16) uint8_t g_perm686[12 * 48];
 // Solved states.

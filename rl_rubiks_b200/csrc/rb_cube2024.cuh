@@ -18,14 +18,162 @@ constexpr int kOhWidth = 480;
 constexpr int kOhVec = kOhWidth / 4;    // 120 float4 per one-hot row
 
 // ---------------------------------------------------------------------------------------------
-// multi_rotate: one move per state.  HBM-bound: 20 B in + 1-2 B action + 20 B out per state.
+// Register LUT.  One move on a cubie-major state is 20 lookups new[j] = lut[a][kind(j)][s[j]] in a 24-entry byte
+// table.  Done through shared memory that is 20 data-dependent LDS.U8 per state with random bank conflicts (the first
+// version of these kernels: 25 % of the HBM roofline).  Here the two 24-byte rows of the state's action sit in 12
+// registers and PRMT is the lookup: for a word of 4 cubie values, selector nibbles (s & 7) pick the candidates from
+// entries 0-7, 8-15 and 16-23, and byte masks made from bit 3 / bit 4 of s (PRMT sign-replicate mode) choose among
+// them: 11 ALU-pipe instructions per 4 lookups, no memory access.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t prmt_r(uint32_t a, uint32_t b, uint32_t sel) {
+	uint32_t r;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+	return r;
+}
+
+struct LutSel {              // per state word, independent of the action: reusable for all 12 actions in expand12
+	uint32_t sel, m1, m2;
+};
+__device__ __forceinline__ LutSel lut_sel(uint32_t w) {
+	LutSel q;
+	const uint32_t t = w & 0x07070707u;
+	const uint32_t y = t | (t >> 4);                           // byte 0 = s0&7 | (s1&7)<<4, byte 2 = s2&7 | (s3&7)<<4
+	q.sel = prmt_r(y, y, 0x3320u);                             // low 16 bits = the four selector nibbles
+	q.m1 = prmt_r(w * 16u, 0u, 0xba98u);                       // 0xff where bit 3 of s is set (entries 8-15)
+	q.m2 = prmt_r(w * 8u, 0u, 0xba98u);                        // 0xff where bit 4 of s is set (entries 16-23)
+	return q;
+}
+// row: the 24-byte table as 6 words (entries 4k..4k+3 in word k)
+__device__ __forceinline__ uint32_t lut24(const uint32_t* __restrict__ row, const LutSel& q) {
+	const uint32_t c0 = prmt_r(row[0], row[1], q.sel), c1 = prmt_r(row[2], row[3], q.sel), c2 = prmt_r(row[4], row[5], q.sel);
+	const uint32_t r = (c1 & q.m1) | (c0 & ~q.m1);
+	return (c2 & q.m2) | (r & ~q.m2);
+}
+// Row fetch.  Lanes of a warp hold different actions, and the 64-byte row pairs of the plain LUT all start in bank
+// group 0 or 4: fetching them with LDS.128 is a 4-way bank conflict.  The kernels below therefore stage the LUT as
+// s_rows[a][k][c] (k = 16-byte chunk of the row pair, c = copy 0..7): lane l reads copy l % 8, which lives in bank group
+// l % 8 whatever its action is -- every fetch is conflict free (6 KB of shared memory).
+constexpr int kRowsX8Vec = 12 * 4 * 8;          // uint4 elements
+__device__ __forceinline__ void stage_rows_x8(uint4* s_rows) {
+	for (int i = threadIdx.x; i < kRowsX8Vec; i += blockDim.x)
+		s_rows[i] = reinterpret_cast<const uint4*>(g_lut2024)[i >> 3];        // i = (a*4 + k)*8 + c  ->  chunk a*4 + k
+}
+// The 12 row words (corner row, edge row) of action a.
+__device__ __forceinline__ void load_rows(const uint4* s_rows, uint32_t a, int lane, uint32_t (&rc)[6], uint32_t (&re)[6]) {
+	const uint4* p = s_rows + a * 32u + (lane & 7);
+	const uint4 c0 = p[0], c1 = p[8], e0 = p[16], e1 = p[24];
+	rc[0] = c0.x; rc[1] = c0.y; rc[2] = c0.z; rc[3] = c0.w; rc[4] = c1.x; rc[5] = c1.y;
+	re[0] = e0.x; re[1] = e0.y; re[2] = e0.z; re[3] = e0.w; re[4] = e1.x; re[5] = e1.y;
+}
+__device__ __forceinline__ void move2024_reg(const uint32_t (&rc)[6], const uint32_t (&re)[6], uint32_t (&w)[5]) {
+	w[0] = lut24(rc, lut_sel(w[0]));
+	w[1] = lut24(rc, lut_sel(w[1]));
+	w[2] = lut24(re, lut_sel(w[2]));
+	w[3] = lut24(re, lut_sel(w[3]));
+	w[4] = lut24(re, lut_sel(w[4]));
+}
+
+// ---------------------------------------------------------------------------------------------
+// State streaming.  32 consecutive states are 640 contiguous bytes = 160 words: a warp moves them with five fully
+// coalesced 128-byte accesses (lane l takes words l, l+32, ...), transposes through 640 bytes of its own shared memory
+// (thread t owns words 5t..5t+4; stride 5 is coprime with the 32 banks: conflict free) and needs no block barrier.
+// Requires 4-byte aligned state arrays; the tile kernels below (`*_any`) take everything else.
+// ---------------------------------------------------------------------------------------------
+constexpr int kWarpsPerBlock = kThreads / 32;
+
+__device__ __forceinline__ void warp_load_states(uint32_t* tile, const uint32_t* __restrict__ src, int words, int lane) {
+#pragma unroll
+	for (int k = 0; k < 5; ++k) {
+		const int i = lane + 32 * k;
+		if (i < words) tile[i] = __ldcs(src + i);
+	}
+	__syncwarp();
+}
+__device__ __forceinline__ void warp_store_states(uint32_t* __restrict__ dst, const uint32_t* tile, int words, int lane) {
+	__syncwarp();
+#pragma unroll
+	for (int k = 0; k < 5; ++k) {
+		const int i = lane + 32 * k;
+		if (i < words) __stcs(dst + i, tile[i]);
+	}
+	__syncwarp();
+}
+
+// multi_rotate: one move per state.  HBM-bound: 20 B in + 1-2 B action + 20 B out per state.  The loads of a warp's next
+// chunk are issued before the current chunk is computed (register double buffer), so every warp always has 640 B in flight.
 __global__ void __launch_bounds__(kThreads)
 k_multi_rotate(const int8_t* __restrict__ in, const uint8_t* __restrict__ faces, const uint8_t* __restrict__ dirs,
                int8_t* __restrict__ out, int64_t n) {
-	__shared__ __align__(16) uint8_t s_lut[RB_LUT_BYTES];
+	__shared__ uint4 s_rows[kRowsX8Vec];
+	__shared__ __align__(16) uint32_t s_tile[kWarpsPerBlock][160];
+	stage_rows_x8(s_rows);
+	__syncthreads();
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	uint32_t* tile = s_tile[wib];
+	const int64_t n_chunks = (n + 31) / 32, stride = (int64_t)gridDim.x * kWarpsPerBlock;
+	uint32_t nxt[5], nf = 0, nd = 0;
+	auto fetch = [&](int64_t c) {                              // chunk c -> registers (words lane, lane+32, ...; action bytes)
+		const int64_t base = c * 32;
+		const int cnt = (int)min((int64_t)32, n - base);
+		const uint32_t* src = reinterpret_cast<const uint32_t*>(in + base * 20);
+#pragma unroll
+		for (int k = 0; k < 5; ++k) nxt[k] = lane + 32 * k < cnt * 5 ? __ldcs(src + lane + 32 * k) : 0u;
+		nf = lane < cnt ? faces[base + lane] : 0u;
+		nd = (dirs && lane < cnt) ? dirs[base + lane] : 0u;
+	};
+	int64_t c = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
+	if (c < n_chunks) fetch(c);
+	for (; c < n_chunks; c += stride) {
+		const int64_t base = c * 32;
+		const int cnt = (int)min((int64_t)32, n - base);
+		const uint32_t a = dirs ? rb_action_of(nf, nd) : rb_clamp_action(nf);
+#pragma unroll
+		for (int k = 0; k < 5; ++k) tile[lane + 32 * k] = nxt[k];
+		if (c + stride < n_chunks) fetch(c + stride);
+		__syncwarp();
+		if (lane < cnt) {
+			uint32_t w[5], rc[6], re[6];
+#pragma unroll
+			for (int k = 0; k < 5; ++k) w[k] = tile[lane * 5 + k];
+			load_rows(s_rows, a, lane, rc, re);
+			move2024_reg(rc, re, w);
+#pragma unroll
+			for (int k = 0; k < 5; ++k) tile[lane * 5 + k] = w[k];
+		}
+		warp_store_states(reinterpret_cast<uint32_t*>(out + base * 20), tile, cnt * 5, lane);
+	}
+}
+
+// multi_is_solved: 20 B in + 1 B out per state.
+__global__ void __launch_bounds__(kThreads)
+k_is_solved(const int8_t* __restrict__ in, uint8_t* __restrict__ flags, int64_t n) {
+	__shared__ __align__(16) uint32_t s_tile[kWarpsPerBlock][160];
+	const uint32_t* sv = reinterpret_cast<const uint32_t*>(g_solved2024);
+	const uint32_t s0 = sv[0], s1 = sv[1], s2 = sv[2], s3 = sv[3], s4 = sv[4];
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	uint32_t* tile = s_tile[wib];
+	const int64_t n_chunks = (n + 31) / 32;
+	for (int64_t c = (int64_t)blockIdx.x * kWarpsPerBlock + wib; c < n_chunks; c += (int64_t)gridDim.x * kWarpsPerBlock) {
+		const int64_t base = c * 32;
+		const int cnt = (int)min((int64_t)32, n - base);
+		warp_load_states(tile, reinterpret_cast<const uint32_t*>(in + base * 20), cnt * 5, lane);
+		if (lane < cnt) {
+			const uint32_t* w = tile + lane * 5;
+			flags[base + lane] = (w[0] == s0) & (w[1] == s1) & (w[2] == s2) & (w[3] == s3) & (w[4] == s4);
+		}
+		__syncwarp();
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// Any-alignment versions (byte views at odd offsets): block tiles staged with whatever vector width the pointer allows.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_multi_rotate_any(const int8_t* __restrict__ in, const uint8_t* __restrict__ faces, const uint8_t* __restrict__ dirs,
+                   int8_t* __restrict__ out, int64_t n) {
+	__shared__ uint4 s_rows[kRowsX8Vec];
 	__shared__ __align__(16) uint32_t s_tile[kTile * 5];
-	rb_stage_lut2024(s_lut);
+	stage_rows_x8(s_rows);
 	const int64_t n_tiles = (n + kTile - 1) / kTile;
 	for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
 		const int64_t base = tile * kTile;
@@ -34,11 +182,12 @@ k_multi_rotate(const int8_t* __restrict__ in, const uint8_t* __restrict__ faces,
 		rb_g2s(reinterpret_cast<uint8_t*>(s_tile), reinterpret_cast<const uint8_t*>(in) + base * 20, cnt * 20);
 		__syncthreads();
 		for (int i = threadIdx.x; i < cnt; i += kThreads) {
-			uint32_t a = dirs ? rb_action_of(faces[base + i], dirs[base + i]) : rb_clamp_action(faces[base + i]);
-			uint32_t w[5];
+			const uint32_t a = dirs ? rb_action_of(faces[base + i], dirs[base + i]) : rb_clamp_action(faces[base + i]);
+			uint32_t w[5], rc[6], re[6];
 #pragma unroll
 			for (int k = 0; k < 5; ++k) w[k] = s_tile[i * 5 + k];
-			rb_move2024(s_lut, a, w);
+			load_rows(s_rows, a, threadIdx.x & 31, rc, re);
+			move2024_reg(rc, re, w);
 #pragma unroll
 			for (int k = 0; k < 5; ++k) s_tile[i * 5 + k] = w[k];
 		}
@@ -47,11 +196,8 @@ k_multi_rotate(const int8_t* __restrict__ in, const uint8_t* __restrict__ faces,
 	}
 }
 
-// ---------------------------------------------------------------------------------------------
-// multi_is_solved
-// ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-k_is_solved(const int8_t* __restrict__ in, uint8_t* __restrict__ flags, int64_t n) {
+k_is_solved_any(const int8_t* __restrict__ in, uint8_t* __restrict__ flags, int64_t n) {
 	__shared__ __align__(16) uint32_t s_tile[kTile * 5];
 	const uint32_t* sv = reinterpret_cast<const uint32_t*>(g_solved2024);
 	const uint32_t s0 = sv[0], s1 = sv[1], s2 = sv[2], s3 = sv[3], s4 = sv[4];
@@ -154,6 +300,75 @@ k_expand12(const int8_t* __restrict__ in, int8_t* __restrict__ children, float* 
 	for (int64_t i = warp; i < n; i += n_warps) {
 		const uint32_t v = warp_load_state(in + i * 20, lane);
 		warp_expand12(s_lut, v, lane, i, children, children_oh, solved);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// expand12, states (+ solved flags) only: 20 B in, 12 x 20 B out per parent, no one-hot to hide behind, so the
+// warp-per-parent kernel above (20 active lanes, byte stores) reaches only 21 % of the roofline.  Here a thread owns a
+// parent: the selector / mask part of the register LUT is computed once per state word and reused for all 12 actions,
+// whose rows are constant-bank operands (every lane applies the same action).  The 240 output bytes of a parent are
+// contiguous; a warp stages its 32 x 240 B in shared memory (row pitch 272 B: 16-byte aligned and conflict free for
+// STS.128) and writes them out as fully coalesced 16-byte vectors.  Needs 16-byte aligned `children`, 4-byte `in`.
+// ---------------------------------------------------------------------------------------------
+constexpr int kExpThreads = 128;                    // 4 warps x 8.5 KB staging
+constexpr int kExpPitch = 68;                       // words per parent row in shared memory (60 used)
+
+__global__ void __launch_bounds__(kExpThreads)
+k_expand12_states(const int8_t* __restrict__ in, int8_t* __restrict__ children, uint8_t* __restrict__ solved, int64_t n) {
+	__shared__ __align__(16) uint32_t s_out[kExpThreads / 32][32 * kExpPitch];
+	__shared__ __align__(16) uint32_t s_in[kExpThreads / 32][160];
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	uint32_t* tile = s_in[wib];
+	uint32_t* stage = s_out[wib];
+	const uint32_t* sv = reinterpret_cast<const uint32_t*>(g_solved2024);
+	const uint32_t v0 = sv[0], v1 = sv[1], v2 = sv[2], v3 = sv[3], v4 = sv[4];
+	const int64_t n_chunks = (n + 31) / 32;
+	constexpr int kW = kExpThreads / 32;
+	for (int64_t c = (int64_t)blockIdx.x * kW + wib; c < n_chunks; c += (int64_t)gridDim.x * kW) {
+		const int64_t base = c * 32;
+		const int cnt = (int)min((int64_t)32, n - base);
+		warp_load_states(tile, reinterpret_cast<const uint32_t*>(in + base * 20), cnt * 5, lane);
+		if (lane < cnt) {
+			LutSel q[5];
+#pragma unroll
+			for (int k = 0; k < 5; ++k) q[k] = lut_sel(tile[lane * 5 + k]);
+			uint32_t flags[3] = {0u, 0u, 0u};
+			uint4* row = reinterpret_cast<uint4*>(stage + lane * kExpPitch);
+#pragma unroll
+			for (int g = 0; g < 3; ++g) {                      // 4 children = 20 words = 5 vectors at a time
+				uint32_t w[20];
+#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					const int a = 4 * g + j;
+					const uint32_t* rc = c_lut2024 + a * 16;
+					const uint32_t* re = rc + 8;
+					w[5 * j + 0] = lut24(rc, q[0]);
+					w[5 * j + 1] = lut24(rc, q[1]);
+					w[5 * j + 2] = lut24(re, q[2]);
+					w[5 * j + 3] = lut24(re, q[3]);
+					w[5 * j + 4] = lut24(re, q[4]);
+					const bool ok = (w[5 * j] == v0) & (w[5 * j + 1] == v1) & (w[5 * j + 2] == v2) & (w[5 * j + 3] == v3) & (w[5 * j + 4] == v4);
+					flags[g] |= (ok ? 1u : 0u) << (8 * j);
+				}
+#pragma unroll
+				for (int v = 0; v < 5; ++v) row[5 * g + v] = make_uint4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
+			}
+			if (solved) {                                      // 12 flag bytes per parent, 4-byte aligned (12 * index)
+				uint32_t* f = reinterpret_cast<uint32_t*>(solved + (base + lane) * 12);
+				f[0] = flags[0]; f[1] = flags[1]; f[2] = flags[2];
+			}
+		}
+		__syncwarp();
+		if (children) {
+			uint4* dst = reinterpret_cast<uint4*>(children + base * 240);
+			const int n_vec = cnt * 15;
+			for (int i = lane; i < n_vec; i += 32) {
+				const int p = (i * 2185) >> 15, r = i - 15 * p;    // i / 15 for i < 480
+				rb_st_stream(dst + i, reinterpret_cast<const uint4*>(stage + p * kExpPitch)[r]);
+			}
+		}
+		__syncwarp();
 	}
 }
 

@@ -25,33 +25,56 @@ __device__ __forceinline__ void copy_record(uint8_t* dst, const uint8_t* src) {
 	d[0] = a; d[1] = b; d[2] = c;
 }
 
-// multi_rotate: 288 B in + action + 288 B out per state; tiles staged through shared memory with 16-byte
-// coalesced global accesses, the permutation applied record by record (thread = one slot of one state).
+// Halfword gather table.  A 6-byte sticker record is 3 halfwords and a state 144 of them; output word j of a move is the
+// halfword pair (2j, 2j+1), each fetched from source halfword perm[a][h / 3] * 3 + h % 3.  s_tab[a][j] holds the two source
+// halfword indices (< 144) as bytes.  28 of the 48 records do not move, so most lanes read consecutive halfwords.
+__device__ __forceinline__ void stage_gather(uint16_t* s_tab) {
+	for (int i = threadIdx.x; i < 12 * 72; i += blockDim.x) {
+		const int a = i / 72, j = i - 72 * a, h0 = 2 * j, h1 = h0 + 1;
+		const uint32_t s0 = g_perm686[a * kSlots + h0 / 3] * 3u + h0 % 3, s1 = g_perm686[a * kSlots + h1 / 3] * 3u + h1 % 3;
+		s_tab[i] = (uint16_t)(s0 | (s1 << 8));
+	}
+}
+// Output word `j` of action `a` applied to the state at `src` (144 halfwords in shared memory).
+__device__ __forceinline__ uint32_t gather_word(const uint16_t* s_tab, const uint16_t* src, uint32_t a, uint32_t j) {
+	const uint32_t pair = s_tab[a * 72u + j];
+	return (uint32_t)src[pair & 0xffu] | ((uint32_t)src[pair >> 8] << 16);
+}
+
+// multi_rotate: 288 B in + action + 288 B out per state.  A warp takes 4 states (288 words = 9 full coalesced rounds)
+// into its own 1152 bytes of shared memory and writes every output word straight from the gather to global memory.
+constexpr int kMrStates = 4;
 __global__ void __launch_bounds__(kThreads)
 k_multi_rotate(const int8_t* __restrict__ in, const uint8_t* __restrict__ faces, const uint8_t* __restrict__ dirs,
                int8_t* __restrict__ out, int64_t n) {
-	__shared__ __align__(16) uint8_t s_perm[12 * 48];
-	__shared__ __align__(16) uint8_t s_in[kTile * kStateBytes];
-	__shared__ __align__(16) uint8_t s_out[kTile * kStateBytes];
-	__shared__ uint8_t s_act[kTile];
-	stage_perm(s_perm);
-	const int64_t n_tiles = (n + kTile - 1) / kTile;
-	for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-		const int64_t base = tile * kTile;
-		const int cnt = (int)min((int64_t)kTile, n - base);
-		__syncthreads();
-		rb_g2s(s_in, reinterpret_cast<const uint8_t*>(in) + base * kStateBytes, cnt * kStateBytes);
-		if (threadIdx.x < cnt)
-			s_act[threadIdx.x] = (uint8_t)(dirs ? rb_action_of(faces[base + threadIdx.x], dirs[base + threadIdx.x])
-			                                    : rb_clamp_action(faces[base + threadIdx.x]));
-		__syncthreads();
-		for (int t = threadIdx.x; t < cnt * kSlots; t += kThreads) {
-			const int st = t / kSlots, slot = t - st * kSlots;
-			const int src = s_perm[s_act[st] * kSlots + slot];
-			copy_record(s_out + st * kStateBytes + slot * 6, s_in + st * kStateBytes + src * 6);
+	__shared__ uint16_t s_tab[12 * 72];
+	__shared__ __align__(16) uint32_t s_buf[kThreads / 32][kMrStates * 72];
+	stage_gather(s_tab);
+	__syncthreads();
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	uint32_t* buf = s_buf[wib];
+	const int64_t n_groups = (n + kMrStates - 1) / kMrStates;
+	for (int64_t g = (int64_t)blockIdx.x * (kThreads / 32) + wib; g < n_groups; g += (int64_t)gridDim.x * (kThreads / 32)) {
+		const int64_t base = g * kMrStates;
+		const int cnt = (int)min((int64_t)kMrStates, n - base), words = cnt * 72;
+		const uint32_t* src = reinterpret_cast<const uint32_t*>(in) + base * 72;
+		uint32_t* dst = reinterpret_cast<uint32_t*>(out) + base * 72;
+		uint32_t a_l = 0;
+		if (lane < cnt) a_l = dirs ? rb_action_of(faces[base + lane], dirs[base + lane]) : rb_clamp_action(faces[base + lane]);
+#pragma unroll
+		for (int r = 0; r < 9; ++r) {
+			const int i = lane + 32 * r;
+			if (i < words) buf[i] = __ldcs(src + i);
 		}
-		__syncthreads();
-		rb_s2g(reinterpret_cast<uint8_t*>(out) + base * kStateBytes, s_out, cnt * kStateBytes);
+		__syncwarp();
+#pragma unroll
+		for (int r = 0; r < 9; ++r) {
+			const int i = lane + 32 * r;
+			const uint32_t st = ((uint32_t)i * 911u) >> 16;            // i / 72 for i < 288
+			const uint32_t a = __shfl_sync(0xffffffffu, a_l, st);
+			if (i < words) __stcs(dst + i, gather_word(s_tab, reinterpret_cast<const uint16_t*>(buf + st * 72u), a, i - 72u * st));
+		}
+		__syncwarp();
 	}
 }
 
@@ -176,6 +199,32 @@ k_expand12(const int8_t* __restrict__ in, int8_t* __restrict__ children, float* 
 			reinterpret_cast<uint4*>(s_buf[wib][0])[lane] = rb_ld_stream(reinterpret_cast<const uint4*>(in + i * kStateBytes) + lane);
 		__syncwarp();
 		warp_expand12(s_buf[wib][1], s_buf[wib][0], s_perm, lane, i, children, children_oh, solved);
+	}
+}
+
+// expand12, children only (288 B in, 12 x 288 B out per parent): the 12 children of a parent are 864 contiguous words =
+// 27 full rounds of a warp; word i is word i % 72 of action i / 72, gathered from the parent held once in shared memory.
+__global__ void __launch_bounds__(kThreads)
+k_expand12_states(const int8_t* __restrict__ in, int8_t* __restrict__ children, int64_t n) {
+	__shared__ uint16_t s_tab[12 * 72];
+	__shared__ __align__(16) uint32_t s_buf[kWarps][72];
+	stage_gather(s_tab);
+	__syncthreads();
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	uint32_t* buf = s_buf[wib];
+	for (int64_t p = (int64_t)blockIdx.x * kWarps + wib; p < n; p += (int64_t)gridDim.x * kWarps) {
+		const uint32_t* src = reinterpret_cast<const uint32_t*>(in) + p * 72;
+		uint32_t* dst = reinterpret_cast<uint32_t*>(children) + p * 864;
+		buf[lane] = __ldcs(src + lane);
+		buf[lane + 32] = __ldcs(src + lane + 32);
+		if (lane < 8) buf[lane + 64] = __ldcs(src + lane + 64);
+		__syncwarp();
+#pragma unroll 9
+		for (int r = 0; r < 27; ++r) {
+			const uint32_t i = lane + 32 * r, a = (i * 911u) >> 16;   // i / 72 for i < 864
+			__stcs(dst + i, gather_word(s_tab, reinterpret_cast<const uint16_t*>(buf), a, i - 72u * a));
+		}
+		__syncwarp();
 	}
 }
 

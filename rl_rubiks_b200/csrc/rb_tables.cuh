@@ -92,6 +92,7 @@ static int ensure_device() {
 	if (done[dev]) return RB_OK;
 	const Tables& t = host();
 	RB_CUDA(cudaMemcpyToSymbol(g_lut2024, t.lut_padded, sizeof(t.lut_padded)));
+	RB_CUDA(cudaMemcpyToSymbol(c_lut2024, t.lut_padded, sizeof(t.lut_padded)));
 	RB_CUDA(cudaMemcpyToSymbol(g_perm686, t.perm686, sizeof(t.perm686)));
 	RB_CUDA(cudaMemcpyToSymbol(g_solved2024, t.solved2024, sizeof(t.solved2024)));
 	RB_CUDA(cudaMemcpyToSymbol(g_solved686, t.solved686, sizeof(t.solved686)));

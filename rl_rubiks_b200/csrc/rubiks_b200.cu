@@ -60,10 +60,14 @@ int rb_multi_rotate(int rep, const int8_t* states, const uint8_t* faces, const u
 	RB_REQUIRE(states && faces && out, "null pointer");
 	RB_INIT();
 	if (rep == RB_REP_2024) {
-		rb2024::k_multi_rotate<<<rb_grid(n, rb2024::kTile, 2), rb2024::kThreads, 0, S(stream)>>>(states, faces, dirs, out, n);
+		if (aligned(states, 4) && aligned(out, 4))
+			rb2024::k_multi_rotate<<<rb_grid(n, 256, 8), rb2024::kThreads, 0, S(stream)>>>(states, faces, dirs, out, n);
+		else
+			rb2024::k_multi_rotate_any<<<rb_grid(n, rb2024::kTile, 2), rb2024::kThreads, 0, S(stream)>>>(states, faces, dirs, out, n);
 		RB_LAUNCHED("multi_rotate_2024");
 	} else {
-		rb686::k_multi_rotate<<<rb_grid(n, rb686::kTile, 4), rb686::kThreads, 0, S(stream)>>>(states, faces, dirs, out, n);
+		RB_REQUIRE(aligned(states, 4) && aligned(out, 4), "6x8x6 states must be 4-byte aligned");
+		rb686::k_multi_rotate<<<rb_grid(n, rb686::kMrStates * rb686::kWarps, 8), rb686::kThreads, 0, S(stream)>>>(states, faces, dirs, out, n);
 		RB_LAUNCHED("multi_rotate_686");
 	}
 	return RB_OK;
@@ -75,7 +79,10 @@ int rb_multi_is_solved(int rep, const int8_t* states, uint8_t* flags, int64_t n,
 	RB_REQUIRE(states && flags, "null pointer");
 	RB_INIT();
 	if (rep == RB_REP_2024) {
-		rb2024::k_is_solved<<<rb_grid(n, rb2024::kTile, 2), rb2024::kThreads, 0, S(stream)>>>(states, flags, n);
+		if (aligned(states, 4))
+			rb2024::k_is_solved<<<rb_grid(n, 256, 8), rb2024::kThreads, 0, S(stream)>>>(states, flags, n);
+		else
+			rb2024::k_is_solved_any<<<rb_grid(n, rb2024::kTile, 2), rb2024::kThreads, 0, S(stream)>>>(states, flags, n);
 		RB_LAUNCHED("is_solved_2024");
 	} else {
 		RB_REQUIRE(aligned(states, 4), "6x8x6 states must be 4-byte aligned");
@@ -120,11 +127,17 @@ int rb_expand12(int rep, const int8_t* states, int8_t* children, float* children
 	RB_REQUIRE(aligned(children_oh, 16), "one-hot output must be 16-byte aligned");
 	RB_INIT();
 	if (rep == RB_REP_2024) {
-		rb2024::k_expand12<<<rb_grid(n, 8, 8), rb2024::kThreads, 0, S(stream)>>>(states, children, children_oh, solved, n);
+		if (!children_oh && aligned(states, 4) && aligned(children, 16) && aligned(solved, 4))
+			rb2024::k_expand12_states<<<rb_grid(n, rb2024::kExpThreads, 5), rb2024::kExpThreads, 0, S(stream)>>>(states, children, solved, n);
+		else
+			rb2024::k_expand12<<<rb_grid(n, 8, 8), rb2024::kThreads, 0, S(stream)>>>(states, children, children_oh, solved, n);
 		RB_LAUNCHED("expand12_2024");
 	} else {
 		RB_REQUIRE(aligned(states, 16) && aligned(children, 16), "6x8x6 states must be 16-byte aligned");
-		rb686::k_expand12<<<rb_grid(n, rb686::kWarps, 6), rb686::kThreads, 0, S(stream)>>>(states, children, children_oh, solved, n);
+		if (!children_oh && !solved)
+			rb686::k_expand12_states<<<rb_grid(n, rb686::kWarps, 8), rb686::kThreads, 0, S(stream)>>>(states, children, n);
+		else
+			rb686::k_expand12<<<rb_grid(n, rb686::kWarps, 6), rb686::kThreads, 0, S(stream)>>>(states, children, children_oh, solved, n);
 		RB_LAUNCHED("expand12_686");
 	}
 	return RB_OK;
