@@ -28,6 +28,9 @@ sys.path.insert(0, ROOT)
 N_CUBES = 1 << 24
 DEPTH = 100
 BYTES_PER_CUBE = DEPTH + 20          # uint8 actions in + int8[20] state out
+# dram__bytes_read.sum + dram__bytes_write.sum of one 2^24-cube launch, from the ncu --set full capture summarised in
+# profiles/r1e_scramble_macro2_lean_ncu.txt (1.677750 GB + 0.321347 GB): the kernel moves exactly its algorithmic bytes.
+NCU_DRAM_BYTES_PER_CUBE = (1.677750e9 + 0.321347e9) / (1 << 24)
 METRIC, UNIT = "cube_moves_per_sec", "moves/s"
 WORKLOAD = "raw scramble: 2^24 cubes x 100 random moves per GPU, 20x24 rep, packed int8 (BASELINE configs[1])"
 
@@ -40,16 +43,44 @@ def measured_peaks():
 
 
 class ClockSampler:
-	"""Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+	"""Samples SM clocks and throttle reasons through NVML (a polling thread, ~1 kHz) while the timed regions run; falls
+	back to `nvidia-smi -lms` when the NVML binding is missing."""
 	Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
 		"clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
 	def __init__(self, index: int):
-		self.index, self.rows, self.proc = index, [], None
+		self.index, self.sm, self.reasons, self.max_mhz = index, [], set(), None
+		self.proc, self.stop, self.thread, self.rows = None, threading.Event(), None, []
+
+	def _poll_nvml(self, nv, h):
+		bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+				"sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+		while not self.stop.is_set():
+			try:
+				self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+				r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+				self.reasons.update(k for k, b in bits.items() if r & b)
+			except Exception:
+				break
+			time.sleep(0.001)
 
 	def __enter__(self):
 		try:
-			self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+			import pynvml as nv
+			nv.nvmlInit()
+			vis, phys = os.environ.get("CUDA_VISIBLE_DEVICES", ""), self.index      # CUDA_VISIBLE_DEVICES may renumber
+			parts = [x.strip() for x in vis.split(",")] if vis else []
+			if self.index < len(parts) and parts[self.index].isdigit():
+				phys = int(parts[self.index])
+			h = nv.nvmlDeviceGetHandleByIndex(phys)
+			self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+			self.thread = threading.Thread(target=self._poll_nvml, args=(nv, h), daemon=True)
+			self.thread.start()
+			return self
+		except Exception:
+			pass
+		try:
+			self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
 										 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
 			self.thread = threading.Thread(target=self._pump, daemon=True)
 			self.thread.start()
@@ -58,51 +89,58 @@ class ClockSampler:
 		return self
 
 	def _pump(self):
+		names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 		for line in self.proc.stdout:
-			self.rows.append([x.strip() for x in line.split(",")])
+			r = [x.strip() for x in line.split(",")]
+			if len(r) >= 6 and r[0].replace(".", "").isdigit():
+				self.sm.append(float(r[0]))
+				self.max_mhz = max(self.max_mhz or 0.0, float(r[1])) if r[1].replace(".", "").isdigit() else self.max_mhz
+				self.reasons.update(n for n, v in zip(names, r[2:6]) if v.lower().startswith("active"))
 
 	def __exit__(self, *exc):
+		self.stop.set()
 		if self.proc:
-			time.sleep(0.15)
+			time.sleep(0.05)
 			self.proc.terminate()
+		if self.thread:
 			self.thread.join(timeout=2)
 
 	def summary(self):
-		sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-		mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
-		names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-		reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-		return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-				"samples": len(sm)}
+		return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+				"samples": len(self.sm)}
 
 
 # ------------------------------------------------------------------------------------------------------------
 # CPU legs: the oracle port (numpy restatement of the reference's algorithm), fanned out over the host cores
 # ------------------------------------------------------------------------------------------------------------
+CPU_CHUNK = 1 << 14          # cubes per numpy call: the (n, depth) int64 draws of a chunk stay cache/RAM friendly
+
+
 def _cpu_worker(args):
-	seed, n, depth = args
+	seed, chunks, depth = args
 	from oracle import cube_oracle as O
 	g = np.random.RandomState(seed)
-	faces, dirs = g.randint(0, 6, (n, depth)), g.randint(0, 2, (n, depth))
+	faces, dirs = g.randint(0, 6, (CPU_CHUNK, depth)), g.randint(0, 2, (CPU_CHUNK, depth))
 	t0 = time.perf_counter()
-	O.scramble_many(faces, dirs, True)
+	for _ in range(chunks):
+		O.scramble_many(faces, dirs, True)
 	return time.perf_counter() - t0
 
 
-def cpu_scramble_throughput(cubes_per_core: int, depth: int, cores: int, pool=None):
-	"""moves/s of the numpy port with `cores` processes each scrambling `cubes_per_core` cubes (wall clock of the slowest)."""
+def cpu_scramble_throughput(chunks_per_core: int, depth: int, cores: int, pool=None):
+	"""moves/s of the numpy port: `cores` processes, each scrambling `chunks_per_core` x 2^14 cubes (wall clock of the slowest)."""
 	import multiprocessing as mp
 	own = pool is None
 	if own:
 		pool = mp.get_context("fork").Pool(cores)
 	try:
 		t0 = time.perf_counter()
-		pool.map(_cpu_worker, [(s, cubes_per_core, depth) for s in range(cores)])
+		pool.map(_cpu_worker, [(s, chunks_per_core, depth) for s in range(cores)])
 		dt = time.perf_counter() - t0
 	finally:
 		if own:
 			pool.close()
-	return cores * cubes_per_core * depth / dt, dt
+	return cores * chunks_per_core * CPU_CHUNK * depth / dt, dt
 
 
 def run_reference(args):
@@ -113,7 +151,7 @@ def run_reference(args):
 		return
 	import multiprocessing as mp
 	cores = os.cpu_count() or 1
-	per_core = 1 << 13
+	per_core = 4                                          # chunks of 2^14 cubes per core and step: ~1 s of CPU work per step
 	pool = mp.get_context("fork").Pool(cores)
 	try:
 		for _ in range(args.warmup):
@@ -124,8 +162,8 @@ def run_reference(args):
 		dt = time.perf_counter() - t0
 	finally:
 		pool.close()
-	value = args.steps * cores * per_core * DEPTH / dt
-	sample = f"{cores} processes x {per_core} cubes x {DEPTH} moves per step (numpy oracle port of cube.py:206-263), extrapolated per move"
+	value = args.steps * cores * per_core * CPU_CHUNK * DEPTH / dt
+	sample = f"{cores} processes x {per_core * CPU_CHUNK} cubes x {DEPTH} moves per step (numpy oracle port of cube.py:206-263), extrapolated per move"
 	print(json.dumps({
 		"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
 		"warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -148,11 +186,11 @@ def run_gpu(args):
 	if world > 1:
 		dist.init_process_group("nccl", device_id=dev)
 	import rl_rubiks_b200  # noqa: F401  (raises if the CUDA library is missing: no CPU fallback)
-	from rl_rubiks_b200 import _native as N, adi, cube
+	from rl_rubiks_b200 import _native as N, adi, cube, sharding
 
 	n, depth = args.cubes, DEPTH
 	gen = torch.Generator(device=dev)
-	gen.manual_seed(1234 + rank)                       # each rank scrambles its own shard of cubes
+	gen.manual_seed(sharding.rank_seed(1234, rank))   # each rank scrambles its own shard of cubes (weak scaling, no collective)
 	actions = torch.randint(0, 12, (n, depth), dtype=torch.uint8, device=dev, generator=gen)
 	out = torch.empty(n, 20, dtype=torch.int8, device=dev)
 	stream = N.stream_handle()
@@ -241,19 +279,21 @@ def run_gpu(args):
 			dist.destroy_process_group()
 		return
 	cores = os.cpu_count() or 1
-	cpu_value, cpu_dt = cpu_scramble_throughput(1 << 14, depth, cores)
+	cpu_chunks = 32                                        # ~10 s of work on every host core
+	cpu_value, cpu_dt = cpu_scramble_throughput(cpu_chunks, depth, cores)
 	result = {
 		"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
 		"ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
 		"data": "synthetic",
 		"config": {"workload": WORKLOAD, "cubes_per_gpu": n, "depth": depth, "actions": "host-supplied uint8 [n][100], resident in HBM",
 				   "l2": "inputs (1.68 GB actions) larger than the 126 MB L2, no reuse between steps", "parity_subsample_ok": parity_ok},
-		"roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-					 "peak_source": peak_src, "kernel": "rbs::k_scramble_macro<3, aligned, double-buffered>", "kernel_ms": kernel_ms,
+		"roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": int(NCU_DRAM_BYTES_PER_CUBE * n),
+					 "traffic_source": "ncu --set full, profiles/r1e_scramble_macro2_lean_ncu.txt (dram read + write per launch, scaled by cubes)",
+					 "peak_source": peak_src, "kernel": "rbs::k_scramble_macro<true>", "kernel_ms": kernel_ms,
 					 "algorithmic_bytes_per_launch": BYTES_PER_CUBE * n,
 					 "note": "multi-move scramble is bound by shared-memory table fetches + PRMT issue, not HBM: see DESIGN.md"},
 		"cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
-						 "sample": f"{cores} processes x {1 << 14} cubes x {depth} moves, numpy oracle port, {cpu_dt:.1f} s"},
+						 "sample": f"{cores} processes x {cpu_chunks * CPU_CHUNK} cubes x {depth} moves, numpy oracle port, {cpu_dt:.1f} s"},
 		"e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * depth, "d2h_bytes_per_step": n * 20,
 				"ms_per_step": float(te.item()) * 1e3, "api": "rbh_scramble (C ABI, pinned host buffers)", "parity_ok": e2e_ok},
 		"gpu_launches": int(launches),

@@ -53,19 +53,27 @@ k_multi_rotate(const int8_t* __restrict__ in, const uint8_t* __restrict__ faces,
 	__syncthreads();
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	uint32_t* buf = s_buf[wib];
-	const int64_t n_groups = (n + kMrStates - 1) / kMrStates;
-	for (int64_t g = (int64_t)blockIdx.x * (kThreads / 32) + wib; g < n_groups; g += (int64_t)gridDim.x * (kThreads / 32)) {
+	const int64_t n_groups = (n + kMrStates - 1) / kMrStates, stride = (int64_t)gridDim.x * (kThreads / 32);
+	uint32_t nxt[9], a_n = 0;
+	auto fetch = [&](int64_t g) {                              // group g -> registers, issued one iteration ahead
 		const int64_t base = g * kMrStates;
 		const int cnt = (int)min((int64_t)kMrStates, n - base), words = cnt * 72;
 		const uint32_t* src = reinterpret_cast<const uint32_t*>(in) + base * 72;
-		uint32_t* dst = reinterpret_cast<uint32_t*>(out) + base * 72;
-		uint32_t a_l = 0;
-		if (lane < cnt) a_l = dirs ? rb_action_of(faces[base + lane], dirs[base + lane]) : rb_clamp_action(faces[base + lane]);
 #pragma unroll
-		for (int r = 0; r < 9; ++r) {
-			const int i = lane + 32 * r;
-			if (i < words) buf[i] = __ldcs(src + i);
-		}
+		for (int r = 0; r < 9; ++r) nxt[r] = lane + 32 * r < words ? __ldcs(src + lane + 32 * r) : 0u;
+		a_n = 0;
+		if (lane < cnt) a_n = dirs ? rb_action_of(faces[base + lane], dirs[base + lane]) : rb_clamp_action(faces[base + lane]);
+	};
+	int64_t g = (int64_t)blockIdx.x * (kThreads / 32) + wib;
+	if (g < n_groups) fetch(g);
+	for (; g < n_groups; g += stride) {
+		const int64_t base = g * kMrStates;
+		const int words = (int)min((int64_t)kMrStates, n - base) * 72;
+		uint32_t* dst = reinterpret_cast<uint32_t*>(out) + base * 72;
+		const uint32_t a_l = a_n;
+#pragma unroll
+		for (int r = 0; r < 9; ++r) buf[lane + 32 * r] = nxt[r];
+		if (g + stride < n_groups) fetch(g + stride);
 		__syncwarp();
 #pragma unroll
 		for (int r = 0; r < 9; ++r) {
@@ -78,23 +86,30 @@ k_multi_rotate(const int8_t* __restrict__ in, const uint8_t* __restrict__ faces,
 	}
 }
 
-// multi_is_solved: compare 72 words per state against the solved state; warp per state.
+// multi_is_solved: 288 B in + 1 B out per state.  A warp takes 4 states = 288 words = 9 full coalesced rounds; each lane
+// collects a 4-bit "differs from solved" mask for the states its words belong to, one warp OR-reduction finishes them.
 __global__ void __launch_bounds__(kThreads)
 k_is_solved(const int8_t* __restrict__ in, uint8_t* __restrict__ flags, int64_t n) {
+	__shared__ uint32_t s_solved[72];
+	if (threadIdx.x < 72) s_solved[threadIdx.x] = reinterpret_cast<const uint32_t*>(g_solved686)[threadIdx.x];
+	__syncthreads();
 	const int lane = threadIdx.x & 31;
-	const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-	const int64_t n_warps = (int64_t)gridDim.x * (kThreads / 32);
-	const uint32_t* sv = reinterpret_cast<const uint32_t*>(g_solved686);
-	for (int64_t i = warp; i < n; i += n_warps) {
-		const uint32_t* p = reinterpret_cast<const uint32_t*>(in + i * kStateBytes);
-		bool ok = true;
+	const int64_t n_groups = (n + 3) / 4;
+	for (int64_t g = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); g < n_groups; g += (int64_t)gridDim.x * (kThreads / 32)) {
+		const int64_t base = g * 4;
+		const int cnt = (int)min((int64_t)4, n - base), words = cnt * 72;
+		const uint32_t* src = reinterpret_cast<const uint32_t*>(in) + base * 72;
+		uint32_t v[9];
 #pragma unroll
-		for (int k = 0; k < 3; ++k) {
-			const int w = lane + 32 * k;
-			if (w < 72) ok &= (p[w] == sv[w]);
+		for (int r = 0; r < 9; ++r) v[r] = lane + 32 * r < words ? __ldcs(src + lane + 32 * r) : 0u;
+		uint32_t bad = 0;
+#pragma unroll
+		for (int r = 0; r < 9; ++r) {
+			const uint32_t i = lane + 32 * r, st = (i * 911u) >> 16;          // i / 72 for i < 288
+			if ((int)i < words && v[r] != s_solved[i - 72u * st]) bad |= 1u << st;
 		}
-		ok = __all_sync(0xffffffffu, ok);
-		if (lane == 0) flags[i] = ok;
+		bad = __reduce_or_sync(0xffffffffu, bad);
+		if (lane < cnt) flags[base + lane] = ((bad >> lane) & 1u) ^ 1u;
 	}
 }
 

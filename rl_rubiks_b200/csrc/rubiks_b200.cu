@@ -86,7 +86,7 @@ int rb_multi_is_solved(int rep, const int8_t* states, uint8_t* flags, int64_t n,
 		RB_LAUNCHED("is_solved_2024");
 	} else {
 		RB_REQUIRE(aligned(states, 4), "6x8x6 states must be 4-byte aligned");
-		rb686::k_is_solved<<<rb_grid(n, rb686::kWarps, 8), rb686::kThreads, 0, S(stream)>>>(states, flags, n);
+		rb686::k_is_solved<<<rb_grid(n, 4 * rb686::kWarps, 8), rb686::kThreads, 0, S(stream)>>>(states, flags, n);
 		RB_LAUNCHED("is_solved_686");
 	}
 	return RB_OK;
