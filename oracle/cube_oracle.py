@@ -519,6 +519,142 @@ class AStarFrontier:
 		self.parents[parent_idcs[sc]] = state_idcs[sc]
 
 
+class MCTSOracle:
+	"""Restatement of MCTS (agents.py:415-645) around `net_fn(oh f32 (n, W)) -> (policy logits (n, 12), values (n,))`.
+	Node arrays are float64 / int as in the reference (agents.py:438-446); the policy goes through an f32 softmax
+	(agents.py:472, 552).  `max_states` is the only stopping rule here (no wall-clock limit)."""
+
+	def __init__(self, net_fn, c: float, search_graph: bool, is2024: bool = True, nu: float = 100):
+		self.net_fn, self.c, self.search_graph, self.is2024, self.nu = net_fn, c, search_graph, is2024, nu
+
+	def __len__(self):
+		return len(self.seen)
+
+	@staticmethod
+	def _softmax32(x):
+		x = np.asarray(x, dtype=np.float32)
+		e = np.exp(x - x.max(axis=1, keepdims=True))
+		return (e / e.sum(axis=1, keepdims=True, dtype=np.float32)).astype(np.float32)
+
+	def _reset(self, n: int, shape):
+		self.seen = SeenSet()
+		self.states = np.empty((n, *shape), dtype=np.int8)
+		self.neighbors = np.zeros((n, 12), dtype=int)
+		self.leaves = np.ones(n, dtype=bool)
+		self.P, self.V = np.empty((n, 12)), np.empty(n)
+		self.N, self.W, self.L = np.zeros((n, 12), dtype=int), np.zeros((n, 12)), np.zeros((n, 12))
+		self.action_queue = []
+
+	def _grow(self):                                      # agents.py:449-458
+		k = len(self.states)
+		self.states = np.concatenate([self.states, np.empty_like(self.states)])
+		self.neighbors = np.concatenate([self.neighbors, np.zeros((k, 12), dtype=int)])
+		self.leaves = np.concatenate([self.leaves, np.ones(k, dtype=bool)])
+		self.P, self.V = np.concatenate([self.P, np.empty((k, 12))]), np.concatenate([self.V, np.empty(k)])
+		self.N = np.concatenate([self.N, np.zeros((k, 12), dtype=int)])
+		self.W, self.L = np.concatenate([self.W, np.zeros((k, 12))]), np.concatenate([self.L, np.zeros((k, 12))])
+
+	def search(self, state: np.ndarray, max_states: int) -> bool:
+		"""agents.py:461-494."""
+		self._reset(1000, state.shape)
+		self.seen.insert_unique(state[None])
+		self.states[1] = state
+		if is_solved(state, self.is2024):
+			return True
+		p, v = self.net_fn(as_oh(state[None], self.is2024))
+		self.P[1], self.V[1] = self._softmax32(p)[0], np.asarray(v).reshape(-1)[0]
+		visited, actions = [1], []
+		while len(self) + 12 <= max_states:
+			leaf, act = self.expand_leaf(visited, actions)
+			if leaf != -1:
+				self.action_queue = list(actions) + [int(act)]
+				if self.search_graph:
+					self.complete_graph()
+					self.shorten_action_queue(leaf)
+				return True
+			visited, actions = self.find_leaf()
+		self.action_queue = list(actions)
+		return False
+
+	def expand_leaf(self, visited: list, actions: list):
+		"""agents.py:496-573."""
+		if len(self) + 12 > len(self.states):
+			self._grow()
+		leaf = visited[-1]
+		sub = expand12(self.states[leaf][None], self.is2024)
+		seen, _, idx = self.seen.insert_unique(sub)
+		new_idx, new_states = idx[~seen], sub[~seen]
+		self.states[new_idx] = new_states
+		acts = np.arange(12)
+		self.neighbors[leaf, acts] = idx
+		self.neighbors[idx, rev_actions(acts)] = leaf
+		self.leaves[leaf] = False
+		solve_leaf = solve_action = -1
+		hit = np.where(multi_is_solved(sub, self.is2024))[0]
+		if hit.size:
+			solve_leaf, solve_action = int(idx[hit[0]]), int(hit[0])
+		p, v = self.net_fn(as_oh(new_states, self.is2024))
+		v = np.asarray(v, dtype=np.float32).reshape(-1)
+		self.P[new_idx] = self._softmax32(p)
+		self.V[new_idx] = v
+		self.W[leaf] = self.V[self.neighbors[leaf]]
+		self.W[new_idx] = np.tile(v, (12, 1)).T
+		if len(v):                                        # the reference raises on an empty batch (v.max() of nothing)
+			self.W[visited[:-1], actions] = np.maximum(self.W[visited[:-1], actions], v.max())
+		if actions:
+			self.N[visited[:-1], actions] += 1
+			self.L[visited[:-1], actions] = 0
+			self.L[visited[1:], rev_actions(np.array(actions))] = 0
+		return solve_leaf, solve_action
+
+	def find_leaf(self):
+		"""agents.py:575-595."""
+		cur, visited, actions = 1, [1], []
+		while not self.leaves[cur]:
+			sqrtN = np.sqrt(self.N[cur].sum())
+			U = self.c * self.P[cur] * sqrtN / (1 + self.N[cur])
+			a = int((U + self.W[cur] - self.L[cur]).argmax())
+			self.L[cur, a] += self.nu
+			cur = int(self.neighbors[cur, a])
+			self.L[cur, rev_action(a)] += self.nu
+			visited.append(cur)
+			actions.append(a)
+		return visited, actions
+
+	def complete_graph(self):
+		"""agents.py:597-611."""
+		leaves = np.where(self.leaves[:len(self) + 1])[0][1:]
+		acts = np.tile(np.arange(12), len(leaves))
+		rep = np.repeat(leaves, 12)
+		idx = self.seen.lookup(expand12(self.states[leaves], self.is2024))
+		self.neighbors[rep, acts] = idx
+		self.neighbors[idx, rev_actions(acts)] = rep
+		self.neighbors[0] = 0
+
+	def shorten_action_queue(self, solved_index: int):
+		"""agents.py:613-633: BFS over the neighbour table from the root to the solved node."""
+		if solved_index == 1:
+			return
+		from collections import deque
+		self.action_queue = []
+		visited = {1: (None, None)}
+		q = deque([1])
+		while q:
+			v = q.popleft()
+			for i, n in enumerate(self.neighbors[v]):
+				n = int(n)
+				if not n or n in visited:
+					continue
+				if n == solved_index:
+					self.action_queue.insert(0, i)
+					while visited[v][0] is not None:
+						self.action_queue.insert(0, visited[v][1])
+						v = visited[v][0]
+					return
+				visited[n] = (v, i)
+				q.append(n)
+
+
 # ---------------------------------------------------------------------------
 # 6x3x3 sticker view, used only to pin the oracle against the literal layouts in
 # the reference's tests/test_cube.py:33-92.  Reference: cube.py:149-173, 279-307,

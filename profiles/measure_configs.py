@@ -75,6 +75,15 @@ def main():
 	want = lambda name: args.only in name
 	g = torch.Generator(device=dev); g.manual_seed(1)
 
+	# ---- calibration: what a pure streaming write / copy reaches on this GPU (torch library kernels, not ours) ----
+	if want("calibration"):
+		buf = torch.empty(2 << 30, dtype=torch.float32, device=dev)
+		report("calibration: torch fill_ 8 GiB (write only)", buf.numel() * 4, buf.numel() * 4, "bytes", lambda: buf.fill_(1.0))
+		half = buf.numel() // 2
+		report("calibration: torch copy_ 4 GiB -> 4 GiB (read + write)", buf.numel() * 4, buf.numel() * 4, "bytes",
+			   lambda: buf[:half].copy_(buf[half:]))
+		del buf
+
 	# ---- C2 raw scramble + companions (20x24) ----
 	if want("scramble_2024"):
 		n, depth = (1 << 24) // q, 100

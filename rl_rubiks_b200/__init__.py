@@ -4,4 +4,4 @@ See DESIGN.md.  Importing requires the built C-ABI library (no CPU fallback)."""
 from . import _native  # noqa: F401  (fails loudly when librubiks_b200.so is missing)
 from . import cube  # noqa: F401
 
-__all__ = ["cube", "adi", "frontier"]
+__all__ = ["cube", "adi", "frontier", "sharding"]

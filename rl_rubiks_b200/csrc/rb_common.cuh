@@ -97,11 +97,21 @@ __device__ __forceinline__ uint32_t rb_clamp_action(uint32_t a) { return a < 12u
 // ---------------------------------------------------------------------------------------------
 // streaming vector access
 // ---------------------------------------------------------------------------------------------
+// Store policy of the big write-once outputs.  0 = st.global.cs (streaming, evict first), 1 = default write-back,
+// 2 = st.global.cg (L2 only).  Tuning knob (RB_STORE_POLICY), uploaded by rbt::ensure_device; default = plain write-back (expand12+oh: 0.91 vs 0.84 of the roofline with .cs).
+__device__ int g_store_policy = 1;
 __device__ __forceinline__ void rb_st_stream(float4* p, float4 v) {
-	// written once, never re-read by this kernel: streaming store
-	__stcs(p, v);
+	const int pol = g_store_policy;
+	if (pol == 0) __stcs(p, v);
+	else if (pol == 1) *p = v;
+	else __stcg(p, v);
 }
-__device__ __forceinline__ void rb_st_stream(uint4* p, uint4 v) { __stcs(p, v); }
+__device__ __forceinline__ void rb_st_stream(uint4* p, uint4 v) {
+	const int pol = g_store_policy;
+	if (pol == 0) __stcs(p, v);
+	else if (pol == 1) *p = v;
+	else __stcg(p, v);
+}
 
 __device__ __forceinline__ uint4 rb_ld_stream(const uint4* p) { return __ldcs(p); }
 

@@ -256,9 +256,43 @@ __device__ __forceinline__ uint32_t warp_move(const uint8_t* s_lut, uint32_t a, 
 	return lane < 20 ? (uint32_t)s_lut[a * 64u + (lane >= 8 ? 32u : 0u) + (v & 31u)] : 0xffu;
 }
 
-// as_oh: HBM-bound, 20 B in + 1920 B out per state.  One warp per state, grid-stride.
+// as_oh: HBM-write-bound, 20 B in + 1920 B out per state.  A block takes tiles of 256 consecutive states (5 words per
+// thread, coalesced, fetched one tile ahead into registers so that the read latency -- several microseconds under a
+// saturating write stream -- is paid once per 480 KB of output and hidden behind it); warp w then emits rows w, w+8, ...
+// of the tile, so the block's eight warps sweep one contiguous region of the output.
 __global__ void __launch_bounds__(kThreads)
 k_as_oh(const int8_t* __restrict__ in, float* __restrict__ oh, int64_t n) {
+	__shared__ __align__(16) uint32_t s_tile[2][kThreads * 5];
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const int64_t n_tiles = (n + kThreads - 1) / kThreads;
+	uint32_t nxt[5];
+	auto fetch = [&](int64_t t) {
+		const int64_t base = t * kThreads;
+		const int words = (int)min((int64_t)kThreads, n - base) * 5;
+		const uint32_t* src = reinterpret_cast<const uint32_t*>(in + base * 20);
+#pragma unroll
+		for (int k = 0; k < 5; ++k) nxt[k] = (int)threadIdx.x + kThreads * k < words ? __ldcs(src + threadIdx.x + kThreads * k) : 0u;
+	};
+	int64_t t = blockIdx.x;
+	if (t < n_tiles) fetch(t);
+	for (int buf = 0; t < n_tiles; t += gridDim.x, buf ^= 1) {
+		const int64_t base = t * kThreads;
+		const int cnt = (int)min((int64_t)kThreads, n - base);
+#pragma unroll
+		for (int k = 0; k < 5; ++k) s_tile[buf][threadIdx.x + kThreads * k] = nxt[k];
+		if (t + gridDim.x < n_tiles) fetch(t + gridDim.x);
+		__syncthreads();                               // tile visible; the other buffer was last read two barriers ago
+		const uint8_t* bytes = reinterpret_cast<const uint8_t*>(s_tile[buf]);
+		for (int r = wib; r < cnt; r += kWarpsPerBlock) {
+			const uint32_t v = lane < 20 ? (uint32_t)bytes[r * 20 + lane] : 0xffu;
+			warp_write_oh_row(oh + (base + r) * kOhWidth, v, lane);
+		}
+	}
+}
+
+// Any-alignment version: one warp per state, byte loads.
+__global__ void __launch_bounds__(kThreads)
+k_as_oh_any(const int8_t* __restrict__ in, float* __restrict__ oh, int64_t n) {
 	const int lane = threadIdx.x & 31;
 	const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
 	const int64_t n_warps = (int64_t)gridDim.x * (kThreads / 32);

@@ -113,19 +113,29 @@ k_is_solved(const int8_t* __restrict__ in, uint8_t* __restrict__ flags, int64_t 
 	}
 }
 
-// as_oh: int8 -> f32 widening of the already one-hot state: 288 B in, 1152 B out.  Thread = 4 bytes -> float4.
+// as_oh: int8 -> f32 widening of the already one-hot state: 288 B in, 1152 B out.  Thread = 4 bytes -> float4, eight
+// independent loads in flight per thread (read latency under a saturating write stream is several microseconds).
 __global__ void __launch_bounds__(kThreads)
 k_as_oh(const int8_t* __restrict__ in, float* __restrict__ oh, int64_t n_words) {
 	const uint32_t* src = reinterpret_cast<const uint32_t*>(in);
 	float4* dst = reinterpret_cast<float4*>(oh);
-	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (int64_t)gridDim.x * blockDim.x) {
-		const uint32_t w = src[i];
-		float4 o;
-		o.x = (float)(int8_t)(w & 0xff);
-		o.y = (float)(int8_t)((w >> 8) & 0xff);
-		o.z = (float)(int8_t)((w >> 16) & 0xff);
-		o.w = (float)(int8_t)(w >> 24);
-		rb_st_stream(dst + i, o);
+	constexpr int kU = 8;
+	const int64_t step = (int64_t)gridDim.x * blockDim.x * kU;
+	for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x * kU + threadIdx.x; i0 < n_words; i0 += step) {
+		uint32_t w[kU];
+#pragma unroll
+		for (int k = 0; k < kU; ++k) w[k] = i0 + k * kThreads < n_words ? __ldcs(src + i0 + k * kThreads) : 0u;
+#pragma unroll
+		for (int k = 0; k < kU; ++k) {
+			if (i0 + k * kThreads < n_words) {
+				float4 o;
+				o.x = (float)(int8_t)(w[k] & 0xff);
+				o.y = (float)(int8_t)((w[k] >> 8) & 0xff);
+				o.z = (float)(int8_t)((w[k] >> 16) & 0xff);
+				o.w = (float)(int8_t)(w[k] >> 24);
+				rb_st_stream(dst + i0 + k * kThreads, o);
+			}
+		}
 	}
 }
 

@@ -99,11 +99,14 @@ int rb_as_oh(int rep, const int8_t* states, float* oh, int64_t n, rb_stream_t st
 	RB_REQUIRE(aligned(oh, 16), "one-hot output must be 16-byte aligned");
 	RB_INIT();
 	if (rep == RB_REP_2024) {
-		rb2024::k_as_oh<<<rb_grid(n, 8, 8), rb2024::kThreads, 0, S(stream)>>>(states, oh, n);
+		if (aligned(states, 4))
+			rb2024::k_as_oh<<<rb_grid(n, rb2024::kThreads, 6), rb2024::kThreads, 0, S(stream)>>>(states, oh, n);
+		else
+			rb2024::k_as_oh_any<<<rb_grid(n, 8, 8), rb2024::kThreads, 0, S(stream)>>>(states, oh, n);
 		RB_LAUNCHED("as_oh_2024");
 	} else {
 		RB_REQUIRE(aligned(states, 4), "6x8x6 states must be 4-byte aligned");
-		rb686::k_as_oh<<<rb_grid(n * 72, rb686::kThreads * 4, 8), rb686::kThreads, 0, S(stream)>>>(states, oh, n * 72);
+		rb686::k_as_oh<<<rb_grid(n * 72, rb686::kThreads * 8, 8), rb686::kThreads, 0, S(stream)>>>(states, oh, n * 72);
 		RB_LAUNCHED("as_oh_686");
 	}
 	return RB_OK;

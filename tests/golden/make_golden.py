@@ -272,6 +272,24 @@ def gen_search():
 	L = len(m)
 	out["mcts_start"], out["mcts_len"] = state, np.int64(L)
 	out["mcts_states"], out["mcts_neighbors"], out["mcts_leaves"] = m.states[1:L + 1].copy(), m.neighbors[:L + 1].copy(), m.leaves[:L + 1].copy()
+	# MCTS full traces with a uniform policy (logits 0 -> softmax exactly 1/12 on any machine) and an integer value net
+	# that counts the cubies in their solved place (exact in f32, tie-heavy):
+	# (a) graph search that finds the solution after ~2300 states (_complete_graph over ~2100 leaves, then
+	#     _shorten_action_queue), (b) tree search cut off by max_states
+	for tag, depth, seed, c, graph, max_states in (("a", 3, 2, 5.0, True, 3000), ("b", 4, 0, 0.6, False, 400)):
+		np.random.seed(seed)
+		state, _, _ = cube.scramble(depth, True)
+		net = FakeNet(480, seed=11, quant=1.0)
+		net.wp[:] = 0
+		net.w[:] = cube.as_oh(cube.get_solved()).cpu().reshape(-1)
+		m = agents.MCTS(net, c=c, search_graph=graph)
+		ok = m.search(state, None, max_states)
+		L = len(m)
+		out[f"mcts{tag}_start"], out[f"mcts{tag}_ok"], out[f"mcts{tag}_len"] = state, np.bool_(ok), np.int64(L)
+		out[f"mcts{tag}_queue"] = np.array(m.action_queue, dtype=np.int64)
+		out[f"mcts{tag}_states"], out[f"mcts{tag}_neighbors"] = m.states[1:L + 1].copy(), m.neighbors[:L + 1].copy()
+		out[f"mcts{tag}_leaves"], out[f"mcts{tag}_N"] = m.leaves[:L + 1].copy(), m.N[:L + 1].copy()
+		out[f"mcts{tag}_W"], out[f"mcts{tag}_V"] = m.W[1:L + 1].copy(), m.V[1:L + 1].copy()
 	save("search", **out)
 
 

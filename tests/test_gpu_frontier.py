@@ -159,3 +159,56 @@ def test_mcts_style_lookup(golden):
 	inner = np.where(~leaves[1:])[0] + 1
 	ch_idx = hs.lookup(O.expand12(states[inner - 1], True)).reshape(-1, 12)
 	assert (ch_idx == nb[inner]).all()
+
+
+class _CountNet(torch.nn.Module):
+	"""The golden MCTS runs' fake net: uniform policy logits, value = number of cubies in their solved place."""
+
+	def __init__(self):
+		super().__init__()
+		self.w = torch.from_numpy(O.as_oh_2024(O.solved_2024()[None])[0]).cuda()
+
+	def forward(self, x, policy=True, value=True):
+		return torch.zeros(x.shape[0], 12, device=x.device), torch.floor(x @ self.w).unsqueeze(1)
+
+
+@pytest.mark.parametrize("tag,c,graph,max_states", [("a", 5.0, True, 3000), ("b", 0.6, False, 400)])
+def test_mcts_full_trace_matches_reference(golden, tag, c, graph, max_states):
+	"""MCTS.search (agents.py:461-633) with the child expansion / dedup / graph completion on the device: node numbering,
+	neighbour table, leaf flags, visit counts, W, V and the action queue equal the trace recorded from the reference."""
+	from rl_rubiks_b200 import cube
+	from rl_rubiks_b200.frontier import MCTS
+	g = golden("search")
+	m = MCTS(_CountNet(), c=c, search_graph=graph)
+	assert m.search(g[f"mcts{tag}_start"], None, max_states) == bool(g[f"mcts{tag}_ok"])
+	L = len(m)
+	assert L == int(g[f"mcts{tag}_len"]) == len(m.hs) and list(m.action_queue) == g[f"mcts{tag}_queue"].tolist()
+	assert (m.states[1:L + 1].cpu().numpy() == g[f"mcts{tag}_states"]).all()
+	assert (m.neighbors[:L + 1] == g[f"mcts{tag}_neighbors"]).all() and (m.leaves[:L + 1] == g[f"mcts{tag}_leaves"]).all()
+	assert (m.N[:L + 1] == g[f"mcts{tag}_N"]).all() and (m.W[1:L + 1] == g[f"mcts{tag}_W"]).all() and (m.V[1:L + 1] == g[f"mcts{tag}_V"]).all()
+	if bool(g[f"mcts{tag}_ok"]):
+		s = g[f"mcts{tag}_start"]
+		for act in m.action_queue:
+			s = cube.rotate(s, *cube.action_space[act])
+		assert cube.is_solved(s)
+
+
+def test_mcts_686_solves_shallow_scramble():
+	"""Same agent on the 6x8x6 representation (no golden trace: the action queue must solve the cube)."""
+	from rl_rubiks_b200 import cube
+	from rl_rubiks_b200.frontier import MCTS
+	cube.set_is2024(False)
+
+	class Net(torch.nn.Module):
+		def forward(self, x, policy=True, value=True):
+			w = torch.from_numpy(O.as_oh_686(O.solved_686()[None])[0]).to(x.device)
+			return torch.zeros(x.shape[0], 12, device=x.device), torch.floor(x @ w).unsqueeze(1)
+
+	s = O.solved_686()
+	for a in (3, 8):
+		s = O.rotate_686(s, a // 2, 1 - a % 2)
+	m = MCTS(Net(), c=0.6, search_graph=True)
+	assert m.search(s, None, 2000)
+	for act in m.action_queue:
+		s = cube.rotate(s, *cube.action_space[act])
+	assert cube.is_solved(s) and len(m) == len(m.hs)

@@ -275,3 +275,23 @@ def test_mcts_indices_and_neighbors(golden):
 		ch_idx = seen.lookup(O.expand12(states[i - 1][None], True))
 		assert (ch_idx == nb[i]).all()
 		assert (nb[nb[i], O.rev_actions(np.arange(12))] == i).all()
+
+
+def _count_net(oh):
+	"""The golden MCTS runs' fake net: uniform policy logits, value = number of cubies in their solved place."""
+	w = O.as_oh_2024(O.solved_2024()[None])[0]
+	return np.zeros((len(oh), 12), np.float32), np.floor(oh @ w)
+
+
+@pytest.mark.parametrize("tag,c,graph,max_states", [("a", 5.0, True, 3000), ("b", 0.6, False, 400)])
+def test_mcts_full_trace(golden, tag, c, graph, max_states):
+	"""MCTS.search end to end (agents.py:461-633): node numbering, neighbour table, leaf flags, visit counts, W, V and
+	the action queue (after graph completion + shortening in case a) equal the reference's."""
+	g = golden("search")
+	m = O.MCTSOracle(_count_net, c=c, search_graph=graph)
+	assert m.search(g[f"mcts{tag}_start"], max_states) == bool(g[f"mcts{tag}_ok"])
+	L = len(m)
+	assert L == int(g[f"mcts{tag}_len"]) and m.action_queue == g[f"mcts{tag}_queue"].tolist()
+	assert (m.states[1:L + 1] == g[f"mcts{tag}_states"]).all()
+	assert (m.neighbors[:L + 1] == g[f"mcts{tag}_neighbors"]).all() and (m.leaves[:L + 1] == g[f"mcts{tag}_leaves"]).all()
+	assert (m.N[:L + 1] == g[f"mcts{tag}_N"]).all() and (m.W[1:L + 1] == g[f"mcts{tag}_W"]).all() and (m.V[1:L + 1] == g[f"mcts{tag}_V"]).all()

@@ -1,0 +1,79 @@
+// Write-bandwidth microbenchmark: which store pattern reaches the fill rate on B200?  8 GiB of float4 per variant.
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+// (a) linear grid-stride: consecutive threads write consecutive float4, whole grid sweeps the buffer front to back
+template <int POL>
+__global__ void k_linear(float4* out, int64_t n_vec) {
+	const float4 v = make_float4(1.f, 0.f, 0.f, 0.f);
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
+		if (POL == 0) __stcs(out + i, v); else out[i] = v;
+	}
+}
+// (b) one 1920-byte row per warp, warps grid-stride over rows (consecutive warps -> consecutive rows)
+template <int POL>
+__global__ void k_rows(float4* out, int64_t n_rows) {
+	const int lane = threadIdx.x & 31;
+	const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+	const float4 v = make_float4(1.f, 0.f, 0.f, 0.f);
+	for (int64_t r = warp; r < n_rows; r += n_warps) {
+		float4* row = out + r * 120;
+#pragma unroll
+		for (int k = 0; k < 4; ++k) if (lane + 32 * k < 120) { if (POL == 0) __stcs(row + lane + 32 * k, v); else row[lane + 32 * k] = v; }
+	}
+}
+// (c) every warp owns a long contiguous span of rows (13 x 1920 B per step, like the fused ADI generator)
+template <int POL>
+__global__ void k_spans(float4* out, int64_t n_rows, int rows_per_warp) {
+	const int lane = threadIdx.x & 31;
+	const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+	const float4 v = make_float4(1.f, 0.f, 0.f, 0.f);
+	for (int64_t r0 = warp * rows_per_warp; r0 < n_rows; r0 += n_warps * rows_per_warp)
+		for (int r = 0; r < rows_per_warp && r0 + r < n_rows; ++r) {
+			float4* row = out + (r0 + r) * 120;
+#pragma unroll
+			for (int k = 0; k < 4; ++k) if (lane + 32 * k < 120) { if (POL == 0) __stcs(row + lane + 32 * k, v); else row[lane + 32 * k] = v; }
+		}
+}
+
+template <class F>
+void time_it(const char* name, F f, double bytes) {
+	cudaEvent_t a, b;
+	cudaEventCreate(&a); cudaEventCreate(&b);
+	f(); f();
+	float best = 1e9f;
+	for (int i = 0; i < 5; ++i) {
+		cudaEventRecord(a); f(); cudaEventRecord(b); cudaEventSynchronize(b);
+		float ms; cudaEventElapsedTime(&ms, a, b);
+		best = ms < best ? ms : best;
+	}
+	printf("%-58s %.3f ms  %.0f GB/s\n", name, best, bytes / best / 1e6);
+}
+
+int main() {
+	const int64_t n_rows = (int64_t)1 << 22;             // x 1920 B = 8.05 GB
+	const int64_t n_vec = n_rows * 120;
+	float4* out;
+	cudaMalloc(&out, n_vec * 16);
+	const double bytes = (double)n_vec * 16;
+	for (int bps : {4, 8, 16}) {
+		char nm[128];
+		snprintf(nm, sizeof nm, "linear .cs   %d blocks/SM x 256", bps); time_it(nm, [&] { k_linear<0><<<148 * bps, 256>>>(out, n_vec); }, bytes);
+		snprintf(nm, sizeof nm, "linear .wb   %d blocks/SM x 256", bps); time_it(nm, [&] { k_linear<1><<<148 * bps, 256>>>(out, n_vec); }, bytes);
+	}
+	time_it("linear .wb   one thread per float4 (huge grid)", [&] { k_linear<1><<<(unsigned)((n_vec + 255) / 256), 256>>>(out, n_vec); }, bytes);
+	for (int bps : {4, 8}) {
+		char nm[128];
+		snprintf(nm, sizeof nm, "row per warp .cs   %d blocks/SM x 256", bps); time_it(nm, [&] { k_rows<0><<<148 * bps, 256>>>(out, n_rows); }, bytes);
+		snprintf(nm, sizeof nm, "row per warp .wb   %d blocks/SM x 256", bps); time_it(nm, [&] { k_rows<1><<<148 * bps, 256>>>(out, n_rows); }, bytes);
+	}
+	for (int rpw : {13, 39, 256}) {
+		char nm[128];
+		snprintf(nm, sizeof nm, "span of %d rows per warp .cs  8 blocks/SM", rpw); time_it(nm, [&] { k_spans<0><<<148 * 8, 256>>>(out, n_rows, rpw); }, bytes);
+		snprintf(nm, sizeof nm, "span of %d rows per warp .wb  8 blocks/SM", rpw); time_it(nm, [&] { k_spans<1><<<148 * 8, 256>>>(out, n_rows, rpw); }, bytes);
+	}
+	cudaMemset(out, 0, n_vec * 16);
+	time_it("cudaMemsetAsync", [&] { cudaMemsetAsync(out, 0, n_vec * 16); }, bytes);
+	return 0;
+}
