@@ -118,6 +118,10 @@ int rb_adi_generate(int rep, const uint8_t* faces, const uint8_t* dirs, int32_t 
 int rb_adi_targets(const float* values, const uint8_t* solved_children, const uint8_t* solved_states,
                    int64_t n, int32_t depth, int32_t reward_method, int64_t* policy, float* value,
                    rb_stream_t stream);
+/* rb_adi_targets and rb_adi_loss_weights in one launch (n = games*depth): train.py:313-333. */
+int rb_adi_targets_weights(const float* values, const uint8_t* solved_children, const uint8_t* solved_states,
+                           int32_t games, int32_t depth, int32_t reward_method, double alpha, double ws,
+                           int64_t* policy, float* value, float* loss_weights, rb_stream_t stream);
 /* Loss weights, train.py:329-333, evaluated in f64 and rounded to f32 like the reference:
  * ((1-alpha) w/ws + alpha/N)(ws+N), w = 1/(1 + i % depth), N = games*depth.  `ws` is the f64 sum of w the
  * caller obtained the reference's way (numpy pairwise sum; rb_adi_weight_sum restates it). */

@@ -43,6 +43,7 @@ SIGNATURES = {
 	"rb_sequence_scramble": (C.c_int, [C.c_int, _p, _p, _i32, _i32, _i32, _p, _p, _p, _p]),
 	"rb_adi_generate": (C.c_int, [C.c_int, _p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p]),
 	"rb_adi_targets": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _p, _p, _p]),
+	"rb_adi_targets_weights": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _f64, _f64, _p, _p, _p, _p]),
 	"rb_adi_weight_sum": (_f64, [_i32, _i32]),
 	"rb_adi_loss_weights": (C.c_int, [_p, _i32, _i32, _f64, _f64, _p]),
 	"rb_hashset_bytes": (_i64, [_i64]),

@@ -72,15 +72,15 @@ class ADIGenerator:
 		return self.oh_states, self.children_oh
 
 	def targets(self, values: torch.Tensor, alpha: float):
-		"""Kernel B + C (train.py:313-333) from the net's values for the children, f32 (12 n,)."""
+		"""Kernel B (train.py:313-333: targets and loss weights in one launch) from the net's values for the children, f32 (12 n,)."""
 		v = values.reshape(-1)
 		if v.dtype != torch.float32 or not v.is_cuda or v.numel() != 12 * self.n:
 			raise IndexError("values must be a float32 CUDA tensor with 12 * games * depth elements")
 		v = v.contiguous()
 		s = N.stream_handle()
-		N.check(N.lib.rb_adi_targets(N.ptr(v), N.ptr(self.solved_children), N.ptr(self.solved_states), self.n, self.depth,
-									 N.REWARD_METHODS[self.reward_method], N.ptr(self.policy_targets), N.ptr(self.value_targets), s))
-		N.check(N.lib.rb_adi_loss_weights(N.ptr(self.loss_weights), self.games, self.depth, float(alpha), self.weight_sum, s))
+		N.check(N.lib.rb_adi_targets_weights(N.ptr(v), N.ptr(self.solved_children), N.ptr(self.solved_states), self.games, self.depth,
+											 N.REWARD_METHODS[self.reward_method], float(alpha), self.weight_sum,
+											 N.ptr(self.policy_targets), N.ptr(self.value_targets), N.ptr(self.loss_weights), s))
 		return self.policy_targets, self.value_targets, self.loss_weights
 
 

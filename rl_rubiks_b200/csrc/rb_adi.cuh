@@ -12,8 +12,9 @@ constexpr int kThreads = 256;
 __global__ void __launch_bounds__(kThreads)
 k_targets(const float* __restrict__ values, const uint8_t* __restrict__ solved_children,
           const uint8_t* __restrict__ solved_states, int64_t n, int depth, int method,
-          int64_t* __restrict__ policy, float* __restrict__ value) {
+          int64_t* __restrict__ policy, float* __restrict__ value, float* __restrict__ weights, double alpha, double ws) {
 	const float win = method == RB_REWARD_REWARD0 ? 0.f : 1.f;
+	const double us = (double)n;
 	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
 		float v[12];
 		const float4* vp = reinterpret_cast<const float4*>(values + i * 12);   // 48 B rows: 16-byte aligned
@@ -38,6 +39,11 @@ k_targets(const float* __restrict__ values, const uint8_t* __restrict__ solved_c
 		else if (method == RB_REWARD_SCHULTZFIX) { if (i % depth == 0) bv = 0.f; }
 		policy[i] = best;
 		value[i] = bv;
+		if (weights) {                                 // loss weights fused in (same arithmetic as k_loss_weights below)
+			const double w = 1.0 / (double)(1 + (int)(i % depth));
+			const double x = __dadd_rn(__ddiv_rn(__dmul_rn(1.0 - alpha, w), ws), __ddiv_rn(__dmul_rn(alpha, 1.0), us));
+			weights[i] = (float)__dmul_rn(x, __dadd_rn(ws, us));
+		}
 	}
 }
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <atomic>
 #include <mutex>
@@ -97,20 +98,24 @@ __device__ __forceinline__ uint32_t rb_clamp_action(uint32_t a) { return a < 12u
 // ---------------------------------------------------------------------------------------------
 // streaming vector access
 // ---------------------------------------------------------------------------------------------
-// Store policy of the big write-once outputs.  0 = st.global.cs (streaming, evict first), 1 = default write-back,
-// 2 = st.global.cg (L2 only).  Tuning knob (RB_STORE_POLICY), uploaded by rbt::ensure_device; default = plain write-back (expand12+oh: 0.91 vs 0.84 of the roofline with .cs).
-__device__ int g_store_policy = 1;
-__device__ __forceinline__ void rb_st_stream(float4* p, float4 v) {
-	const int pol = g_store_policy;
-	if (pol == 0) __stcs(p, v);
-	else if (pol == 1) *p = v;
-	else __stcg(p, v);
+// Store policy of the big write-once outputs: 0 = st.global.cs (streaming, evict first), 1 = plain write-back.
+// Measured on B200 (profiles/r1i_configs.md vs r1g): outputs of several GB are 5-8 % faster with plain stores, outputs of a
+// few hundred MB (one ADI rollout, one sequence batch) up to 17 % faster with .cs, so the launcher picks by output size
+// (rb_store_policy); RB_STORE_POLICY=0|1 overrides.
+#define RB_STORE_CS 0
+#define RB_STORE_WB 1
+__device__ __forceinline__ void rb_st_stream(float4* p, float4 v, int pol) {
+	if (pol == RB_STORE_CS) __stcs(p, v);
+	else *p = v;
 }
-__device__ __forceinline__ void rb_st_stream(uint4* p, uint4 v) {
-	const int pol = g_store_policy;
-	if (pol == 0) __stcs(p, v);
-	else if (pol == 1) *p = v;
-	else __stcg(p, v);
+__device__ __forceinline__ void rb_st_stream(uint4* p, uint4 v, int pol) {
+	if (pol == RB_STORE_CS) __stcs(p, v);
+	else *p = v;
+}
+static inline int rb_store_policy(int64_t out_bytes) {
+	static const int forced = [] { const char* e = getenv("RB_STORE_POLICY"); return e ? atoi(e) : -1; }();
+	if (forced == 0 || forced == 1) return forced;
+	return out_bytes >= (int64_t(1) << 31) ? RB_STORE_WB : RB_STORE_CS;
 }
 
 __device__ __forceinline__ uint4 rb_ld_stream(const uint4* p) { return __ldcs(p); }
@@ -135,7 +140,7 @@ __device__ __forceinline__ void rb_s2g(uint8_t* g, const uint8_t* s, int nbytes)
 	if ((reinterpret_cast<uintptr_t>(g) & 15u) == 0) {
 		int nv = nbytes >> 4;
 		for (int i = threadIdx.x; i < nv; i += blockDim.x)
-			rb_st_stream(reinterpret_cast<uint4*>(g) + i, reinterpret_cast<const uint4*>(s)[i]);
+			rb_st_stream(reinterpret_cast<uint4*>(g) + i, reinterpret_cast<const uint4*>(s)[i], RB_STORE_CS);
 		for (int i = (nv << 4) + threadIdx.x; i < nbytes; i += blockDim.x) g[i] = s[i];
 	} else if ((reinterpret_cast<uintptr_t>(g) & 3u) == 0) {
 		int nv = nbytes >> 2;

@@ -221,7 +221,7 @@ k_is_solved_any(const int8_t* __restrict__ in, uint8_t* __restrict__ flags, int6
 // floats are (v_j - 4*(c%6) == 0,1,2,3).  `v` is the cubie value held by lane j (lanes 0..19); every
 // element of the row is written (no zero-fill pass, no index tensors), one coalesced 512-byte store per step.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void warp_write_oh_row(float* __restrict__ row, uint32_t v, int lane) {
+__device__ __forceinline__ void warp_write_oh_row(float* __restrict__ row, uint32_t v, int lane, int pol) {
 	float4* dst = reinterpret_cast<float4*>(row);
 #pragma unroll
 	for (int k = 0; k < 4; ++k) {
@@ -235,7 +235,7 @@ __device__ __forceinline__ void warp_write_oh_row(float* __restrict__ row, uint3
 			o.y = off == 1u ? 1.f : 0.f;
 			o.z = off == 2u ? 1.f : 0.f;
 			o.w = off == 3u ? 1.f : 0.f;
-			rb_st_stream(dst + c, o);
+			rb_st_stream(dst + c, o, pol);
 		}
 	}
 }
@@ -261,7 +261,7 @@ __device__ __forceinline__ uint32_t warp_move(const uint8_t* s_lut, uint32_t a, 
 // saturating write stream -- is paid once per 480 KB of output and hidden behind it); warp w then emits rows w, w+8, ...
 // of the tile, so the block's eight warps sweep one contiguous region of the output.
 __global__ void __launch_bounds__(kThreads)
-k_as_oh(const int8_t* __restrict__ in, float* __restrict__ oh, int64_t n) {
+k_as_oh(const int8_t* __restrict__ in, float* __restrict__ oh, int64_t n, int pol) {
 	__shared__ __align__(16) uint32_t s_tile[2][kThreads * 5];
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	const int64_t n_tiles = (n + kThreads - 1) / kThreads;
@@ -285,20 +285,20 @@ k_as_oh(const int8_t* __restrict__ in, float* __restrict__ oh, int64_t n) {
 		const uint8_t* bytes = reinterpret_cast<const uint8_t*>(s_tile[buf]);
 		for (int r = wib; r < cnt; r += kWarpsPerBlock) {
 			const uint32_t v = lane < 20 ? (uint32_t)bytes[r * 20 + lane] : 0xffu;
-			warp_write_oh_row(oh + (base + r) * kOhWidth, v, lane);
+			warp_write_oh_row(oh + (base + r) * kOhWidth, v, lane, pol);
 		}
 	}
 }
 
 // Any-alignment version: one warp per state, byte loads.
 __global__ void __launch_bounds__(kThreads)
-k_as_oh_any(const int8_t* __restrict__ in, float* __restrict__ oh, int64_t n) {
+k_as_oh_any(const int8_t* __restrict__ in, float* __restrict__ oh, int64_t n, int pol) {
 	const int lane = threadIdx.x & 31;
 	const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
 	const int64_t n_warps = (int64_t)gridDim.x * (kThreads / 32);
 	for (int64_t i = warp; i < n; i += n_warps) {
 		const uint32_t v = warp_load_state(in + i * 20, lane);
-		warp_write_oh_row(oh + i * kOhWidth, v, lane);
+		warp_write_oh_row(oh + i * kOhWidth, v, lane, pol);
 	}
 }
 
@@ -308,13 +308,13 @@ k_as_oh_any(const int8_t* __restrict__ in, float* __restrict__ oh, int64_t n) {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void warp_expand12(const uint8_t* s_lut, uint32_t v, int lane, int64_t parent,
                                               int8_t* __restrict__ children, float* __restrict__ children_oh,
-                                              uint8_t* __restrict__ solved) {
+                                              uint8_t* __restrict__ solved, int pol) {
 #pragma unroll 4
 	for (uint32_t a = 0; a < 12; ++a) {
 		const uint32_t c = warp_move(s_lut, a, v, lane);
 		const int64_t row = parent * 12 + a;
 		if (children && lane < 20) children[row * 20 + lane] = (int8_t)c;
-		if (children_oh) warp_write_oh_row(children_oh + row * kOhWidth, c, lane);
+		if (children_oh) warp_write_oh_row(children_oh + row * kOhWidth, c, lane, pol);
 		if (solved) {
 			const bool s = warp_is_solved(c, lane);
 			if (lane == 0) solved[row] = s;
@@ -324,7 +324,7 @@ __device__ __forceinline__ void warp_expand12(const uint8_t* s_lut, uint32_t v, 
 
 __global__ void __launch_bounds__(kThreads)
 k_expand12(const int8_t* __restrict__ in, int8_t* __restrict__ children, float* __restrict__ children_oh,
-           uint8_t* __restrict__ solved, int64_t n) {
+           uint8_t* __restrict__ solved, int64_t n, int pol) {
 	__shared__ __align__(16) uint8_t s_lut[RB_LUT_BYTES];
 	rb_stage_lut2024(s_lut);
 	__syncthreads();
@@ -333,7 +333,7 @@ k_expand12(const int8_t* __restrict__ in, int8_t* __restrict__ children, float* 
 	const int64_t n_warps = (int64_t)gridDim.x * (kThreads / 32);
 	for (int64_t i = warp; i < n; i += n_warps) {
 		const uint32_t v = warp_load_state(in + i * 20, lane);
-		warp_expand12(s_lut, v, lane, i, children, children_oh, solved);
+		warp_expand12(s_lut, v, lane, i, children, children_oh, solved, pol);
 	}
 }
 
@@ -349,7 +349,7 @@ constexpr int kExpThreads = 128;                    // 4 warps x 8.5 KB staging
 constexpr int kExpPitch = 68;                       // words per parent row in shared memory (60 used)
 
 __global__ void __launch_bounds__(kExpThreads)
-k_expand12_states(const int8_t* __restrict__ in, int8_t* __restrict__ children, uint8_t* __restrict__ solved, int64_t n) {
+k_expand12_states(const int8_t* __restrict__ in, int8_t* __restrict__ children, uint8_t* __restrict__ solved, int64_t n, int pol) {
 	__shared__ __align__(16) uint32_t s_out[kExpThreads / 32][32 * kExpPitch];
 	__shared__ __align__(16) uint32_t s_in[kExpThreads / 32][160];
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -399,7 +399,7 @@ k_expand12_states(const int8_t* __restrict__ in, int8_t* __restrict__ children, 
 			const int n_vec = cnt * 15;
 			for (int i = lane; i < n_vec; i += 32) {
 				const int p = (i * 2185) >> 15, r = i - 15 * p;    // i / 15 for i < 480
-				rb_st_stream(dst + i, reinterpret_cast<const uint4*>(stage + p * kExpPitch)[r]);
+				rb_st_stream(dst + i, reinterpret_cast<const uint4*>(stage + p * kExpPitch)[r], pol);
 			}
 		}
 		__syncwarp();
@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(kThreads)
 k_sequence(const uint8_t* __restrict__ faces, const uint8_t* __restrict__ dirs, int games, int depth,
            int with_solved, int chunk, int8_t* __restrict__ states, float* __restrict__ oh,
            uint8_t* __restrict__ solved_states, int8_t* __restrict__ children, float* __restrict__ children_oh,
-           uint8_t* __restrict__ solved_children) {
+           uint8_t* __restrict__ solved_children, int pol) {
 	__shared__ __align__(16) uint8_t s_lut[RB_LUT_BYTES];
 	rb_stage_lut2024(s_lut);
 	__syncthreads();
@@ -497,12 +497,12 @@ k_sequence(const uint8_t* __restrict__ faces, const uint8_t* __restrict__ dirs, 
 			}
 			const int64_t row = (int64_t)g * depth + d;
 			if (states && lane < 20) states[row * 20 + lane] = (int8_t)v;
-			if (oh) warp_write_oh_row(oh + row * kOhWidth, v, lane);
+			if (oh) warp_write_oh_row(oh + row * kOhWidth, v, lane, pol);
 			if (solved_states) {
 				const bool s = warp_is_solved(v, lane);
 				if (lane == 0) solved_states[row] = s;
 			}
-			if (kChildren) warp_expand12(s_lut, v, lane, row, children, children_oh, solved_children);
+			if (kChildren) warp_expand12(s_lut, v, lane, row, children, children_oh, solved_children, pol);
 		}
 	}
 }

@@ -116,7 +116,7 @@ k_is_solved(const int8_t* __restrict__ in, uint8_t* __restrict__ flags, int64_t 
 // as_oh: int8 -> f32 widening of the already one-hot state: 288 B in, 1152 B out.  Thread = 4 bytes -> float4, eight
 // independent loads in flight per thread (read latency under a saturating write stream is several microseconds).
 __global__ void __launch_bounds__(kThreads)
-k_as_oh(const int8_t* __restrict__ in, float* __restrict__ oh, int64_t n_words) {
+k_as_oh(const int8_t* __restrict__ in, float* __restrict__ oh, int64_t n_words, int pol) {
 	const uint32_t* src = reinterpret_cast<const uint32_t*>(in);
 	float4* dst = reinterpret_cast<float4*>(oh);
 	constexpr int kU = 8;
@@ -133,7 +133,7 @@ k_as_oh(const int8_t* __restrict__ in, float* __restrict__ oh, int64_t n_words) 
 				o.y = (float)(int8_t)((w[k] >> 8) & 0xff);
 				o.z = (float)(int8_t)((w[k] >> 16) & 0xff);
 				o.w = (float)(int8_t)(w[k] >> 24);
-				rb_st_stream(dst + i0 + k * kThreads, o);
+				rb_st_stream(dst + i0 + k * kThreads, o, pol);
 			}
 		}
 	}
@@ -158,9 +158,9 @@ k_as_correct(const float* __restrict__ oh, float* __restrict__ out, int64_t n_sl
 
 // Emit one state held in shared memory (288 B at `s`): raw bytes, f32 one-hot row and solved flag; warp-wide.
 __device__ __forceinline__ void warp_emit(const uint8_t* s, int lane, int64_t row, int8_t* __restrict__ states,
-                                          float* __restrict__ oh, uint8_t* __restrict__ solved) {
+                                          float* __restrict__ oh, uint8_t* __restrict__ solved, int pol) {
 	if (states && lane < 18)
-		rb_st_stream(reinterpret_cast<uint4*>(states + row * kStateBytes) + lane, reinterpret_cast<const uint4*>(s)[lane]);
+		rb_st_stream(reinterpret_cast<uint4*>(states + row * kStateBytes) + lane, reinterpret_cast<const uint4*>(s)[lane], pol);
 	if (oh) {
 		float4* dst = reinterpret_cast<float4*>(oh + row * kStateBytes);
 #pragma unroll
@@ -173,7 +173,7 @@ __device__ __forceinline__ void warp_emit(const uint8_t* s, int lane, int64_t ro
 				o.y = (float)(int8_t)((x >> 8) & 0xff);
 				o.z = (float)(int8_t)((x >> 16) & 0xff);
 				o.w = (float)(int8_t)(x >> 24);
-				rb_st_stream(dst + w, o);
+				rb_st_stream(dst + w, o, pol);
 			}
 		}
 	}
@@ -201,17 +201,17 @@ constexpr int kWarps = kThreads / 32;
 // expand12 (+ one-hot + solved): warp per parent; parent and one child buffer per warp in shared memory.
 __device__ __forceinline__ void warp_expand12(uint8_t* child, const uint8_t* parent, const uint8_t* s_perm, int lane,
                                               int64_t prow, int8_t* __restrict__ children, float* __restrict__ children_oh,
-                                              uint8_t* __restrict__ solved) {
+                                              uint8_t* __restrict__ solved, int pol) {
 	for (uint32_t a = 0; a < 12; ++a) {
 		warp_move(child, parent, s_perm, a, lane);
-		warp_emit(child, lane, prow * 12 + a, children, children_oh, solved);
+		warp_emit(child, lane, prow * 12 + a, children, children_oh, solved, pol);
 		__syncwarp();
 	}
 }
 
 __global__ void __launch_bounds__(kThreads)
 k_expand12(const int8_t* __restrict__ in, int8_t* __restrict__ children, float* __restrict__ children_oh,
-           uint8_t* __restrict__ solved, int64_t n) {
+           uint8_t* __restrict__ solved, int64_t n, int pol) {
 	__shared__ __align__(16) uint8_t s_perm[12 * 48];
 	__shared__ __align__(16) uint8_t s_buf[kWarps][2][kStateBytes];
 	stage_perm(s_perm);
@@ -223,7 +223,7 @@ k_expand12(const int8_t* __restrict__ in, int8_t* __restrict__ children, float* 
 		if (lane < 18)
 			reinterpret_cast<uint4*>(s_buf[wib][0])[lane] = rb_ld_stream(reinterpret_cast<const uint4*>(in + i * kStateBytes) + lane);
 		__syncwarp();
-		warp_expand12(s_buf[wib][1], s_buf[wib][0], s_perm, lane, i, children, children_oh, solved);
+		warp_expand12(s_buf[wib][1], s_buf[wib][0], s_perm, lane, i, children, children_oh, solved, pol);
 	}
 }
 
@@ -279,7 +279,7 @@ k_scramble(const uint8_t* __restrict__ actions, int64_t stride_cube, int64_t str
 			}
 		}
 		if (lane < 18)
-			rb_st_stream(reinterpret_cast<uint4*>(out + i * kStateBytes) + lane, reinterpret_cast<const uint4*>(s_buf[wib][cur])[lane]);
+			rb_st_stream(reinterpret_cast<uint4*>(out + i * kStateBytes) + lane, reinterpret_cast<const uint4*>(s_buf[wib][cur])[lane], RB_STORE_CS);
 		__syncwarp();
 	}
 }
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(kThreads)
 k_sequence(const uint8_t* __restrict__ faces, const uint8_t* __restrict__ dirs, int games, int depth,
            int with_solved, int chunk, int8_t* __restrict__ states, float* __restrict__ oh,
            uint8_t* __restrict__ solved_states, int8_t* __restrict__ children, float* __restrict__ children_oh,
-           uint8_t* __restrict__ solved_children) {
+           uint8_t* __restrict__ solved_children, int pol) {
 	__shared__ __align__(16) uint8_t s_perm[12 * 48];
 	__shared__ __align__(16) uint8_t s_buf[kWarps][3][kStateBytes];
 	stage_perm(s_perm);
@@ -328,8 +328,8 @@ k_sequence(const uint8_t* __restrict__ faces, const uint8_t* __restrict__ dirs, 
 				++applied;
 			}
 			const int64_t row = (int64_t)g * depth + d;
-			warp_emit(s_buf[wib][cur], lane, row, states, oh, solved_states);
-			if (kChildren) warp_expand12(s_buf[wib][2], s_buf[wib][cur], s_perm, lane, row, children, children_oh, solved_children);
+			warp_emit(s_buf[wib][cur], lane, row, states, oh, solved_states, pol);
+			if (kChildren) warp_expand12(s_buf[wib][2], s_buf[wib][cur], s_perm, lane, row, children, children_oh, solved_children, pol);
 			__syncwarp();
 		}
 	}

@@ -97,10 +97,6 @@ static int ensure_device() {
 	RB_CUDA(cudaMemcpyToSymbol(g_perm686, t.perm686, sizeof(t.perm686)));
 	RB_CUDA(cudaMemcpyToSymbol(g_solved2024, t.solved2024, sizeof(t.solved2024)));
 	RB_CUDA(cudaMemcpyToSymbol(g_solved686, t.solved686, sizeof(t.solved686)));
-	if (const char* e = getenv("RB_STORE_POLICY")) {
-		const int pol = atoi(e);
-		RB_CUDA(cudaMemcpyToSymbol(g_store_policy, &pol, sizeof(pol)));
-	}
 	done[dev] = true;
 	return RB_OK;
 }

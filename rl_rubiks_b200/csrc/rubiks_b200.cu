@@ -100,13 +100,13 @@ int rb_as_oh(int rep, const int8_t* states, float* oh, int64_t n, rb_stream_t st
 	RB_INIT();
 	if (rep == RB_REP_2024) {
 		if (aligned(states, 4))
-			rb2024::k_as_oh<<<rb_grid(n, rb2024::kThreads, 6), rb2024::kThreads, 0, S(stream)>>>(states, oh, n);
+			rb2024::k_as_oh<<<rb_grid(n, rb2024::kThreads, 6), rb2024::kThreads, 0, S(stream)>>>(states, oh, n, rb_store_policy(n * 1920));
 		else
-			rb2024::k_as_oh_any<<<rb_grid(n, 8, 8), rb2024::kThreads, 0, S(stream)>>>(states, oh, n);
+			rb2024::k_as_oh_any<<<rb_grid(n, 8, 8), rb2024::kThreads, 0, S(stream)>>>(states, oh, n, rb_store_policy(n * 1920));
 		RB_LAUNCHED("as_oh_2024");
 	} else {
 		RB_REQUIRE(aligned(states, 4), "6x8x6 states must be 4-byte aligned");
-		rb686::k_as_oh<<<rb_grid(n * 72, rb686::kThreads * 8, 8), rb686::kThreads, 0, S(stream)>>>(states, oh, n * 72);
+		rb686::k_as_oh<<<rb_grid(n * 72, rb686::kThreads * 8, 8), rb686::kThreads, 0, S(stream)>>>(states, oh, n * 72, rb_store_policy(n * 1152));
 		RB_LAUNCHED("as_oh_686");
 	}
 	return RB_OK;
@@ -131,16 +131,18 @@ int rb_expand12(int rep, const int8_t* states, int8_t* children, float* children
 	RB_INIT();
 	if (rep == RB_REP_2024) {
 		if (!children_oh && aligned(states, 4) && aligned(children, 16) && aligned(solved, 4))
-			rb2024::k_expand12_states<<<rb_grid(n, rb2024::kExpThreads, 5), rb2024::kExpThreads, 0, S(stream)>>>(states, children, solved, n);
+			rb2024::k_expand12_states<<<rb_grid(n, rb2024::kExpThreads, 5), rb2024::kExpThreads, 0, S(stream)>>>(states, children, solved, n, rb_store_policy(n * 240));
 		else
-			rb2024::k_expand12<<<rb_grid(n, 8, 8), rb2024::kThreads, 0, S(stream)>>>(states, children, children_oh, solved, n);
+			rb2024::k_expand12<<<rb_grid(n, 8, 8), rb2024::kThreads, 0, S(stream)>>>(states, children, children_oh, solved, n,
+			                                                                             rb_store_policy(children_oh ? n * 12 * 1920 : n * 240));
 		RB_LAUNCHED("expand12_2024");
 	} else {
 		RB_REQUIRE(aligned(states, 16) && aligned(children, 16), "6x8x6 states must be 16-byte aligned");
 		if (!children_oh && !solved)
 			rb686::k_expand12_states<<<rb_grid(n, rb686::kWarps, 8), rb686::kThreads, 0, S(stream)>>>(states, children, n);
 		else
-			rb686::k_expand12<<<rb_grid(n, rb686::kWarps, 6), rb686::kThreads, 0, S(stream)>>>(states, children, children_oh, solved, n);
+			rb686::k_expand12<<<rb_grid(n, rb686::kWarps, 6), rb686::kThreads, 0, S(stream)>>>(states, children, children_oh, solved, n,
+			                                                                                 rb_store_policy(n * 12 * (children_oh ? 1440 : 288)));
 		RB_LAUNCHED("expand12_686");
 	}
 	return RB_OK;
@@ -187,24 +189,26 @@ static int launch_sequence(int rep, bool with_children, const uint8_t* faces, co
 	const int ws = with_solved ? 1 : 0;
 	const int chunk = sequence_chunk(games, depth);
 	const int64_t units = (int64_t)games * ((depth + chunk - 1) / chunk);
+	const int64_t rows = (int64_t)games * depth * (with_children ? 13 : 1);
+	const int pol = rb_store_policy(rows * (rep == RB_REP_2024 ? ((oh || children_oh) ? 1920 : 20) : ((oh || children_oh) ? 1440 : 288)));
 	if (rep == RB_REP_2024) {
 		const int grid = rb_grid(units, 8, 8);
 		if (with_children)
 			rb2024::k_sequence<true><<<grid, rb2024::kThreads, 0, S(stream)>>>(faces, dirs, games, depth, ws, chunk, states, oh,
-			                                                               solved_states, children, children_oh, solved_children);
+			                                                               solved_states, children, children_oh, solved_children, pol);
 		else
 			rb2024::k_sequence<false><<<grid, rb2024::kThreads, 0, S(stream)>>>(faces, dirs, games, depth, ws, chunk, states, oh,
-			                                                                solved_states, nullptr, nullptr, nullptr);
+			                                                                solved_states, nullptr, nullptr, nullptr, pol);
 		RB_LAUNCHED("sequence_2024");
 	} else {
 		RB_REQUIRE(aligned(states, 16) && aligned(children, 16), "6x8x6 states must be 16-byte aligned");
 		const int grid = rb_grid(units, rb686::kWarps, 6);
 		if (with_children)
 			rb686::k_sequence<true><<<grid, rb686::kThreads, 0, S(stream)>>>(faces, dirs, games, depth, ws, chunk, states, oh,
-			                                                              solved_states, children, children_oh, solved_children);
+			                                                              solved_states, children, children_oh, solved_children, pol);
 		else
 			rb686::k_sequence<false><<<grid, rb686::kThreads, 0, S(stream)>>>(faces, dirs, games, depth, ws, chunk, states, oh,
-			                                                               solved_states, nullptr, nullptr, nullptr);
+			                                                               solved_states, nullptr, nullptr, nullptr, pol);
 		RB_LAUNCHED("sequence_686");
 	}
 	return RB_OK;
@@ -222,8 +226,9 @@ int rb_adi_generate(int rep, const uint8_t* faces, const uint8_t* dirs, int32_t 
 	                       children_oh, solved_children, stream);
 }
 
-int rb_adi_targets(const float* values, const uint8_t* solved_children, const uint8_t* solved_states, int64_t n,
-                   int32_t depth, int32_t reward_method, int64_t* policy, float* value, rb_stream_t stream) {
+static int adi_targets_impl(const float* values, const uint8_t* solved_children, const uint8_t* solved_states, int64_t n,
+                            int32_t depth, int32_t reward_method, int64_t* policy, float* value, float* weights, double alpha,
+                            double ws, rb_stream_t stream) {
 	RB_REQUIRE(n >= 0 && depth > 0, "bad size");
 	RB_REQUIRE(reward_method >= RB_REWARD_PAPER && reward_method <= RB_REWARD_REWARD0, "unknown reward method");
 	if (n == 0) return RB_OK;
@@ -231,9 +236,22 @@ int rb_adi_targets(const float* values, const uint8_t* solved_children, const ui
 	RB_REQUIRE(reward_method != RB_REWARD_LAPANFIX || solved_states, "lapanfix needs solved_states");
 	RB_REQUIRE(aligned(values, 16) && aligned(solved_children, 4), "values must be 16-byte and flags 4-byte aligned");
 	rbadi::k_targets<<<rb_grid(n, rbadi::kThreads, 8), rbadi::kThreads, 0, S(stream)>>>(values, solved_children, solved_states, n,
-	                                                                             depth, reward_method, policy, value);
+	                                                                             depth, reward_method, policy, value, weights, alpha, ws);
 	RB_LAUNCHED("adi_targets");
 	return RB_OK;
+}
+
+int rb_adi_targets(const float* values, const uint8_t* solved_children, const uint8_t* solved_states, int64_t n,
+                   int32_t depth, int32_t reward_method, int64_t* policy, float* value, rb_stream_t stream) {
+	return adi_targets_impl(values, solved_children, solved_states, n, depth, reward_method, policy, value, nullptr, 0.0, 1.0, stream);
+}
+
+int rb_adi_targets_weights(const float* values, const uint8_t* solved_children, const uint8_t* solved_states, int32_t games,
+                           int32_t depth, int32_t reward_method, double alpha, double ws, int64_t* policy, float* value,
+                           float* loss_weights, rb_stream_t stream) {
+	RB_REQUIRE(games >= 0 && loss_weights, "bad size or null loss_weights");
+	return adi_targets_impl(values, solved_children, solved_states, (int64_t)games * depth, depth, reward_method, policy, value,
+	                        loss_weights, alpha, ws, stream);
 }
 
 double rb_adi_weight_sum(int32_t games, int32_t depth) {
