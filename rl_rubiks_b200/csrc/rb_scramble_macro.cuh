@@ -40,7 +40,7 @@ constexpr int kP2Bytes = kDevRows * 32 * 4;     // 4-byte part, 32 copies (one p
 constexpr int kTableBytes = kP1Bytes + kP2Bytes;        // 65,536
 constexpr int kMaxThreads = 1024;               // 32 warps (CUDA limit per CTA)
 constexpr int kSmemBudget = 227 * 1024;
-constexpr int kReduceEvery = 10;                // rows between twist folds: 10 + 10 * 2 <= 31
+constexpr int kReduceEvery = 10;                // rows between twist folds (5 action words): 10 + 10 * 2 <= 31
 
 __device__ __align__(16) uint32_t g_macro[kRows * kRowWords + 3];
 
@@ -287,20 +287,27 @@ k_scramble_macro(const uint8_t* __restrict__ actions, int8_t* __restrict__ out, 
 		if ((int)lane < cnt) {
 			uint8_t* row = buf + lane * depth;
 			Slots s{0x60402000u, 0xe0c0a080u, 0x03020100u, 0x07060504u, 0x0b0a0908u};
-			int m = 0, steps = 0;
-#pragma unroll 2
-			for (; m + 4 <= depth; m += 4) {                           // 4 moves = 1 word = 2 rows
-				uint32_t w;
-				if (kWordAligned) w = *reinterpret_cast<const uint32_t*>(row + m);
-				else w = row[m] | (row[m + 1] << 8) | (row[m + 2] << 16) | ((uint32_t)row[m + 3] << 24);
+			// 4 moves = 1 action word = 2 table rows.  Groups of 5 words are fully unrolled (immediate offsets, no loop
+			// bookkeeping on the ALU pipe that bounds this kernel) and end with the twist fold: 10 rows add at most 20.
+			auto word_at = [&](int m) -> uint32_t {
+				if (kWordAligned) return *reinterpret_cast<const uint32_t*>(row + m);
+				return row[m] | (row[m + 1] << 8) | (row[m + 2] << 16) | ((uint32_t)row[m + 3] << 24);
+			};
+			auto apply_word = [&](uint32_t w) {
 				w &= 0x0f0f0f0fu;                                       // any byte stays inside the 256-row table (valid input: 0..11)
 				apply_at(table, row_offset(__dp4a(w, 0x00000D01u, 0u), lane_off), d2, s);
 				apply_at(table, row_offset(__dp4a(w, 0x0D010000u, 0u), lane_off), d2, s);
-				if ((steps += 2) == kReduceEvery) { steps = 0; s.C0 = fold_twists(s.C0); s.C1 = fold_twists(s.C1); }
-			}
-			if (m < depth) {                                           // up to 3 trailing moves, identity padded
+			};
+			int m = 0;
+			for (; m + 20 <= depth; m += 20) {
+				const uint32_t w0 = word_at(m), w1 = word_at(m + 4), w2 = word_at(m + 8), w3 = word_at(m + 12), w4 = word_at(m + 16);
+				apply_word(w0); apply_word(w1); apply_word(w2); apply_word(w3); apply_word(w4);
 				s.C0 = fold_twists(s.C0); s.C1 = fold_twists(s.C1);
-				for (; m < depth; m += 2) {
+			}
+			if (m < depth) {
+				for (; m + 4 <= depth; m += 4) apply_word(word_at(m));     // at most 4 words = 8 rows
+				s.C0 = fold_twists(s.C0); s.C1 = fold_twists(s.C1);
+				for (; m < depth; m += 2) {                                // up to 3 trailing moves, identity padded
 					const uint32_t a0 = row[m], a1 = m + 1 < depth ? row[m + 1] : 12u;
 					apply_at(table, row_offset((a0 & 15u) + 13u * (a1 & 15u), lane_off), d2, s);
 				}

@@ -38,6 +38,15 @@ __device__ __forceinline__ void op8(uint32_t (&r)[8], uint32_t s, uint32_t t) {
 			else asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(t), "r"(s));
 		}
 		if (OP == 13) asm volatile("mul.lo.u32 %0, %0, 0x010D0000;" : "+r"(r[i]));                       // IMAD (mul.lo imm)
+		if (OP == 15) { uint32_t lo, hi; asm volatile("{ .reg .b64 w; mul.wide.u32 w, %2, %3; mov.b64 {%0, %1}, w; }" : "=r"(lo), "=r"(hi) : "r"(r[i]), "r"(t)); r[i] = hi ^ lo; }   // IMAD.WIDE by a register (+ LOP)
+		if (OP == 19) { uint32_t hi; asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(hi) : "r"(r[i]), "r"(t)); r[i] = hi; }   // IMAD.HI by a register
+		if (OP == 16) asm volatile("shf.r.clamp.b32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(s), "r"(t));       // SHF funnel
+		if (OP == 17) asm volatile("bfe.u32 %0, %0, 16, 16;" : "+r"(r[i]));                                 // BFE
+		if (OP == 18) asm volatile("shr.u32 %0, %0, %1;" : "+r"(r[i]) : "r"(t));                            // SHF by register
+		if (OP == 20) asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(r[i]) : "r"(r[(i + 1) & 7]), "r"(r[(i + 3) & 7]), "r"(r[(i + 5) & 7]));   // PRMT, 3 fresh regs
+		if (OP == 21) asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(r[i]) : "r"(r[(i + 1) & 7]), "r"(r[(i + 2) & 7]), "r"(s));                   // PRMT, 2 fresh regs
+		if (OP == 22) asm volatile("lop3.b32 %0, %1, %2, %3, 0x78;" : "=r"(r[i]) : "r"(r[(i + 1) & 7]), "r"(r[(i + 3) & 7]), "r"(r[(i + 5) & 7])); // LOP3, 3 fresh regs
+		if (OP == 23) asm volatile("lop3.b32 %0, %1, 0x10101010, %2, 0x78;" : "=r"(r[i]) : "r"(r[(i + 1) & 7]), "r"(r[(i + 3) & 7]));             // LOP3, 2 fresh + imm
 		if (OP == 14) asm volatile("vmin4.u32.u32.u32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(s), "r"(t)); // emulated SIMD min
 	}
 }
@@ -64,8 +73,8 @@ void run(const char* name) {
 	cudaMalloc(&out, 148 * 1024 * 4); cudaMalloc(&cyc, 148 * 32 * 8);
 	for (int warps_per_smsp : {1, 2, 4, 8}) {
 		const int threads = warps_per_smsp * 4 * 32;
-		k<OP><<<148, threads>>>(out, cyc, 0x3210, 7);
-		k<OP><<<148, threads>>>(out, cyc, 0x3210, 7);
+		k<OP><<<148, threads>>>(out, cyc, 0x3210, 65536 + 7);
+		k<OP><<<148, threads>>>(out, cyc, 0x3210, 65536 + 7);
 		cudaDeviceSynchronize();
 		long long h[148 * 32];
 		cudaMemcpy(h, cyc, sizeof(long long) * 148 * threads / 32, cudaMemcpyDeviceToHost);
@@ -88,6 +97,15 @@ int main() {
 	run<7>("IDP.4A");
 	run<8>("SHF");
 	run<14>("vmin4 (emulated)");
+	run<20>("PRMT 3 fresh regs");
+	run<21>("PRMT 2 fresh regs");
+	run<22>("LOP3 3 fresh regs");
+	run<23>("LOP3 2 fresh + imm");
+	run<15>("IMAD.WIDE reg + LOP");
+	run<19>("IMAD.HI reg");
+	run<16>("SHF funnel");
+	run<17>("BFE 16,16");
+	run<18>("SHR by reg");
 	run<9>("PRMT+IMAD.HI 1:1");
 	run<10>("PRMT+IMAD 1:1");
 	run<11>("PRMT+LOP3 1:1");
