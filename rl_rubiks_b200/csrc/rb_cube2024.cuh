@@ -507,4 +507,96 @@ k_sequence(const uint8_t* __restrict__ faces, const uint8_t* __restrict__ dirs, 
 	}
 }
 
+// ---------------------------------------------------------------------------------------------
+// sequence_scramble without one-hot (states and/or solved flags only: 21 B per move).  With no 1920-byte row to hide
+// behind, the warp-per-game kernel above (20 of 32 lanes, byte stores) reaches 4 % of the roofline; here a thread owns a
+// game and a warp 32 consecutive games.  The state stays cubie-major in 5 registers, a move is the register LUT, the
+// actions of the next 8 moves are prefetched while the current 8 are applied, and every 8 positions the warp flushes
+// 32 x 160 contiguous bytes per game from shared memory (pitch 41 words: conflict free) in coalesced words.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSeqGroup = 8;                    // positions staged per flush
+constexpr int kSeqPitch = kSeqGroup * 5 + 1;    // words per game in the staging tile
+
+__global__ void __launch_bounds__(kThreads)
+k_sequence_states(const uint8_t* __restrict__ faces, const uint8_t* __restrict__ dirs, int games, int depth, int with_solved,
+                  int8_t* __restrict__ states, uint8_t* __restrict__ solved_states) {
+	__shared__ uint4 s_rows[kRowsX8Vec];
+	__shared__ uint32_t s_stage[kWarpsPerBlock][32 * kSeqPitch];
+	stage_rows_x8(s_rows);
+	__syncthreads();
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	uint32_t* stage = s_stage[wib];
+	const uint32_t* sv = reinterpret_cast<const uint32_t*>(g_solved2024);
+	const uint32_t v0 = sv[0], v1 = sv[1], v2 = sv[2], v3 = sv[3], v4 = sv[4];
+	const int n_warps_games = (games + 31) / 32;
+	const int moves = depth - with_solved;                     // action rows used: 0 .. moves-1
+	for (int wg = blockIdx.x * kWarpsPerBlock + wib; wg < n_warps_games; wg += gridDim.x * kWarpsPerBlock) {
+		const int g0 = wg * 32, g = g0 + lane, cnt = min(32, games - g0);
+		const bool live = lane < cnt;
+		uint32_t w[5] = {v0, v1, v2, v3, v4};
+		uint32_t act[kSeqGroup];
+		auto fetch = [&](int m0) {                             // actions of moves m0 .. m0+7 of this lane's game (coalesced over lanes)
+#pragma unroll
+			for (int k = 0; k < kSeqGroup; ++k) {
+				const int m = m0 + k;
+				uint32_t a = 12u;
+				if (live && m >= 0 && m < moves) {
+					const int64_t idx = (int64_t)m * games + g;
+					a = dirs ? rb_action_of(faces[idx], dirs[idx]) : rb_clamp_action(faces[idx]);
+				}
+				act[k] = a;
+			}
+		};
+		// position d holds the state after d + 1 - with_solved moves: with_solved shifts the moves by one position
+		fetch(-with_solved);
+		for (int d0 = 0; d0 < depth; d0 += kSeqGroup) {
+			uint32_t cur[kSeqGroup];
+#pragma unroll
+			for (int k = 0; k < kSeqGroup; ++k) cur[k] = act[k];
+			if (d0 + kSeqGroup < depth) fetch(d0 + kSeqGroup - with_solved);
+			uint32_t flags_lo = 0, flags_hi = 0;
+#pragma unroll
+			for (int k = 0; k < kSeqGroup; ++k) {
+				const int d = d0 + k;
+				if (d < depth) {
+					if (cur[k] < 12u) {                        // 12 = no move (the leading solved position / padding)
+						uint32_t rc[6], re[6];
+						load_rows(s_rows, cur[k], lane, rc, re);
+						move2024_reg(rc, re, w);
+					}
+#pragma unroll
+					for (int q = 0; q < 5; ++q) stage[lane * kSeqPitch + k * 5 + q] = w[q];
+					const uint32_t ok = (w[0] == v0) & (w[1] == v1) & (w[2] == v2) & (w[3] == v3) & (w[4] == v4);
+					if (k < 4) flags_lo |= ok << (8 * k); else flags_hi |= ok << (8 * (k - 4));
+				}
+			}
+			__syncwarp();
+			const int npos = min(kSeqGroup, depth - d0), per_game = npos * 5;
+			if (states) {
+				uint32_t* out_w = reinterpret_cast<uint32_t*>(states) + ((int64_t)g0 * depth + d0) * 5;
+				const int64_t game_pitch = (int64_t)depth * 5;
+				if (npos == kSeqGroup) {                           // full group: 40 words per game, constant division
+#pragma unroll 4
+					for (int i = lane; i < cnt * (kSeqGroup * 5); i += 32) {
+						const int gi = (i * 1639) >> 16, k = i - gi * (kSeqGroup * 5);      // i / 40 for i < 1280
+						__stcs(out_w + gi * game_pitch + k, stage[gi * kSeqPitch + k]);
+					}
+				} else {
+					for (int i = lane; i < cnt * per_game; i += 32) {
+						const int gi = i / per_game, k = i - gi * per_game;
+						out_w[gi * game_pitch + k] = stage[gi * kSeqPitch + k];
+					}
+				}
+			}
+			if (solved_states && live) {
+				uint8_t* f = solved_states + (int64_t)g * depth + d0;
+#pragma unroll
+				for (int k = 0; k < kSeqGroup; ++k)
+					if (k < npos) f[k] = (uint8_t)(((k < 4 ? flags_lo : flags_hi) >> (8 * (k & 3))) & 1u);
+			}
+			__syncwarp();
+		}
+	}
+}
+
 }  // namespace rb2024

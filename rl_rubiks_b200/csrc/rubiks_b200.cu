@@ -191,7 +191,12 @@ static int launch_sequence(int rep, bool with_children, const uint8_t* faces, co
 	const int64_t units = (int64_t)games * ((depth + chunk - 1) / chunk);
 	const int64_t rows = (int64_t)games * depth * (with_children ? 13 : 1);
 	const int pol = rb_store_policy(rows * (rep == RB_REP_2024 ? ((oh || children_oh) ? 1920 : 20) : ((oh || children_oh) ? 1440 : 288)));
-	if (rep == RB_REP_2024) {
+	if (rep == RB_REP_2024 && !with_children && !oh && aligned(states, 4)) {
+		// states / flags only: thread per game, register LUT, staged coalesced output
+		rb2024::k_sequence_states<<<rb_grid(games, rb2024::kThreads, 4), rb2024::kThreads, 0, S(stream)>>>(faces, dirs, games, depth, ws,
+		                                                                                             states, solved_states);
+		RB_LAUNCHED("sequence_states_2024");
+	} else if (rep == RB_REP_2024) {
 		const int grid = rb_grid(units, 8, 8);
 		if (with_children)
 			rb2024::k_sequence<true><<<grid, rb2024::kThreads, 0, S(stream)>>>(faces, dirs, games, depth, ws, chunk, states, oh,

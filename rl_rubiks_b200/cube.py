@@ -317,17 +317,23 @@ def scramble(depth: int, force_not_solved=False):
 	return state, faces, dirs
 
 
-def sequence_scrambler_from(faces, dirs, with_solved: bool, device_out: bool = False):
-	"""`sequence_scrambler` with the (depth, games) draws supplied by the caller."""
+def sequence_scrambler_from(faces, dirs, with_solved: bool, device_out: bool = False, with_oh: bool = True,
+							with_flags: bool = False):
+	"""`sequence_scrambler` with the (depth, games) draws supplied by the caller.  `with_oh=False` skips the one-hot
+	(states-only fast kernel); `with_flags` also returns the solved flag of every emitted state."""
 	faces, dirs = np.asarray(faces), np.asarray(dirs)
 	depth, games = faces.shape
 	a = torch.from_numpy(_actions_u8(faces, dirs)).to(_dev())
 	n = games * depth
 	states = torch.empty(n, *shape(), dtype=torch.int8, device=a.device)
-	oh = torch.empty(n, get_oh_shape(), dtype=torch.float32, device=a.device)
+	oh = torch.empty(n, get_oh_shape(), dtype=torch.float32, device=a.device) if with_oh else None
+	flags = torch.empty(n, dtype=torch.uint8, device=a.device) if with_flags else None
 	N.check(N.lib.rb_sequence_scramble(_rep(), N.ptr(a), None, games, depth, int(bool(with_solved)), N.ptr(states), N.ptr(oh),
-									   None, N.stream_handle()))
-	return (states if device_out else states.cpu().numpy()), oh
+									   N.ptr(flags), N.stream_handle()))
+	res = [states if device_out else states.cpu().numpy(), oh]
+	if with_flags:
+		res.append(flags.bool() if device_out else flags.bool().cpu().numpy())
+	return tuple(res)
 
 
 def sequence_scrambler(games: int, depth: int, with_solved: bool):
