@@ -57,6 +57,8 @@ __device__ __align__(16) uint8_t g_lut2024[12 * 2 * 32];
 __constant__ uint32_t c_lut2024[12 * 16];
 // g_perm686[a*48 + slot] = source sticker slot.
 __device__ __align__(16) uint8_t g_perm686[12 * 48];
+// Sticker tables for rendering a 6x8x6 state from a 20x24 one: [cubie][value][k] destination slot, then [cubie][k] home slot.
+__device__ __align__(16) uint8_t g_stickers686[20 * 24 * 3 + 20 * 3 + 4];
 // Solved states.
 __device__ __align__(16) uint8_t g_solved2024[32];     // 20 used, padded to 8 words
 __device__ __align__(16) uint8_t g_solved686[288];

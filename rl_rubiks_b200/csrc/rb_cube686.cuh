@@ -284,6 +284,53 @@ k_scramble(const uint8_t* __restrict__ actions, int64_t stride_cube, int64_t str
 	}
 }
 
+// Render: 6x8x6 state of a move sequence from the 20x24 state of the SAME sequence.  Moves only permute sticker records,
+// so "start, then the sequence" = start gathered through the sequence's net permutation, and that permutation is what
+// the 20x24 state encodes: cubie c with value v carries its sticker k from its home slot to slot dst[c][v][k] (tables
+// derived in rb_tables.cuh by running both representations side by side).  This lets the 6x8x6 scramble run on the
+// slot-major macro-move kernel (rb_scramble_macro.cuh) instead of moving 288 bytes through shared memory per move.
+// In place: the 20x24 state is parked in the first 20 bytes of each 288-byte output row.  Warp per cube.
+constexpr int kStickerDst = 20 * 24 * 3, kStickerBytes = kStickerDst + 20 * 3 + 4;
+__global__ void __launch_bounds__(kThreads)
+k_render_from2024(int8_t* __restrict__ io, const int8_t* __restrict__ start, int64_t n) {
+	__shared__ __align__(16) uint8_t s_tab[kStickerBytes];
+	__shared__ __align__(16) uint8_t s_out[kWarps][kStateBytes];
+	__shared__ __align__(16) uint8_t s_src[kWarps][kStateBytes];
+	for (int i = threadIdx.x; i < kStickerBytes / 4; i += blockDim.x)
+		reinterpret_cast<uint32_t*>(s_tab)[i] = reinterpret_cast<const uint32_t*>(g_stickers686)[i];
+	__syncthreads();
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	for (int64_t i = (int64_t)blockIdx.x * kWarps + wib; i < n; i += (int64_t)gridDim.x * kWarps) {
+		int8_t* row = io + i * kStateBytes;
+		const uint32_t v = lane < 20 ? (uint32_t)(uint8_t)row[lane] : 0u;
+		if (start && lane < 18) reinterpret_cast<uint4*>(s_src[wib])[lane] = rb_ld_stream(reinterpret_cast<const uint4*>(start + i * kStateBytes) + lane);
+		__syncwarp();
+#pragma unroll
+		for (int r = 0; r < 2; ++r) {
+			const int j = lane + 32 * r;                           // sticker index: 24 corner stickers, then 24 edge stickers
+			const int c = j < 24 ? j / 3 : 8 + ((j - 24) >> 1), k = j < 24 ? j - 3 * (j / 3) : (j - 24) & 1;
+			uint32_t val = __shfl_sync(0xffffffffu, v, c < 20 ? c : 0);
+			if (j < 48) {
+				val = val < 24u ? val : 0u;
+				const uint32_t dst = s_tab[(c * 24 + val) * 3 + k], src = s_tab[kStickerDst + c * 3 + k];
+				uint16_t h0, h1, h2;
+				if (start) {
+					const uint16_t* q = reinterpret_cast<const uint16_t*>(s_src[wib] + src * 6);
+					h0 = q[0]; h1 = q[1]; h2 = q[2];
+				} else {                                           // solved start: one-hot of the home face's colour
+					const uint32_t face = src >> 3, bit = 1u << (8 * (face & 1u));
+					h0 = (uint16_t)((face >> 1) == 0 ? bit : 0); h1 = (uint16_t)((face >> 1) == 1 ? bit : 0); h2 = (uint16_t)((face >> 1) == 2 ? bit : 0);
+				}
+				uint16_t* o = reinterpret_cast<uint16_t*>(s_out[wib] + dst * 6);
+				o[0] = h0; o[1] = h1; o[2] = h2;
+			}
+		}
+		__syncwarp();
+		if (lane < 18) rb_st_stream(reinterpret_cast<uint4*>(row) + lane, reinterpret_cast<const uint4*>(s_out[wib])[lane], RB_STORE_CS);
+		__syncwarp();
+	}
+}
+
 // sequence_scramble / fused ADI generator: same unit decomposition as the 20x24 kernel (game, chunk of depth).
 template <bool kChildren>
 __global__ void __launch_bounds__(kThreads)

@@ -245,7 +245,7 @@ __device__ __forceinline__ void store_state(uint8_t* __restrict__ o, const Slots
 // The finished state overwrites the first 20 bytes of the thread's own (consumed) action row.
 template <bool kWordAligned>
 __global__ void __launch_bounds__(kMaxThreads, 1)
-k_scramble_macro(const uint8_t* __restrict__ actions, int8_t* __restrict__ out, int64_t n, int depth) {
+k_scramble_macro(const uint8_t* __restrict__ actions, int8_t* __restrict__ out, int64_t n, int depth, int out_pitch) {
 	extern __shared__ __align__(128) uint8_t smem[];
 	uint8_t* table = smem;
 	uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTableBytes);
@@ -317,16 +317,17 @@ k_scramble_macro(const uint8_t* __restrict__ actions, int8_t* __restrict__ out, 
 		__syncwarp();
 		// copy out: word k of cube c sits at buf + c*depth + 4k; consecutive lanes write consecutive global words
 		{
-			uint8_t* dst = reinterpret_cast<uint8_t*>(out) + chunk * 32 * 20;
+			// out_pitch = 20 for the 20x24 output; 288 when the state is parked at the head of a 6x8x6 row (rb686 render)
+			uint8_t* dst = reinterpret_cast<uint8_t*>(out) + chunk * 32 * out_pitch;
 			if (kWordAligned && (reinterpret_cast<uintptr_t>(out) & 3u) == 0) {
 				for (int i = lane; i < cnt * 5; i += 32) {
 					const int c = i / 5, k = i - 5 * c;
-					reinterpret_cast<uint32_t*>(dst)[i] = *reinterpret_cast<const uint32_t*>(buf + c * depth + 4 * k);
+					*reinterpret_cast<uint32_t*>(dst + c * out_pitch + 4 * k) = *reinterpret_cast<const uint32_t*>(buf + c * depth + 4 * k);
 				}
 			} else {
 				for (int i = lane; i < cnt * 20; i += 32) {
 					const int c = i / 20, k = i - 20 * c;
-					dst[i] = buf[c * depth + k];
+					dst[c * out_pitch + k] = buf[c * depth + k];
 				}
 			}
 		}
@@ -379,15 +380,15 @@ static int warps_for(int64_t n, int depth) {
 	return (int)w;
 }
 
-static int launch(const uint8_t* actions, int8_t* out, int64_t n, int depth, cudaStream_t st) {
+static int launch(const uint8_t* actions, int8_t* out, int64_t n, int depth, cudaStream_t st, int out_pitch = 20) {
 	int rc = ensure_device();
 	if (rc != RB_OK) return rc;
 	const int W = warps_for(n, depth);
 	const int64_t ctas = ((n + 31) / 32 + W - 1) / W;
 	const int grid = (int)(ctas < RB_NUM_SMS ? ctas : RB_NUM_SMS);
 	const size_t smem = (size_t)kFixedSmem + (size_t)W * 32 * depth;
-	if (depth % 4 == 0) k_scramble_macro<true><<<grid, W * 32, smem, st>>>(actions, out, n, depth);
-	else k_scramble_macro<false><<<grid, W * 32, smem, st>>>(actions, out, n, depth);
+	if (depth % 4 == 0) k_scramble_macro<true><<<grid, W * 32, smem, st>>>(actions, out, n, depth, out_pitch);
+	else k_scramble_macro<false><<<grid, W * 32, smem, st>>>(actions, out, n, depth, out_pitch);
 	RB_LAUNCHED("scramble_macro_2024");
 	return RB_OK;
 }

@@ -24,6 +24,12 @@ struct Tables {
 	uint8_t perm686[12][48];      // gather table over the 48 sticker slots
 	uint8_t solved2024[32];
 	uint8_t solved686[288];
+	// Sticker view of the cubies (derived below by running both representations side by side): the 6x8x6 slot of sticker k
+	// of corner cubie c / edge cubie e at home, and its slot when the cubie's 20x24 value is v.  Used to render a 6x8x6
+	// state from the 20x24 state of the same move sequence (rb686 fast scramble).
+	uint8_t corner_home[8][3], corner_dst[8][24][3];
+	uint8_t edge_home[12][2], edge_dst[12][24][2];
+	bool stickers_ok;
 };
 
 static void build(Tables& t) {
@@ -75,10 +81,83 @@ static void build(Tables& t) {
 		for (int p = 0; p < 8; ++p) t.solved686[(f * 8 + p) * 6 + f] = 1;
 }
 
+// Follows one cubie through all 24 (position, orientation) values with the 20x24 LUT while moving its stickers with the
+// 6x8x6 slot permutations; `dst[v][k]` = slot of sticker k when the cubie's value is v.  Returns false on any inconsistency
+// between the two representations.
+template <int K>
+static bool follow_cubie(const Tables& t, int kind, int home_value, const uint8_t (&home)[K], uint8_t (*dst)[K]) {
+	bool seen[24] = {};
+	int queue[24], head = 0, tail = 0;
+	for (int k = 0; k < K; ++k) dst[home_value][k] = home[k];
+	seen[home_value] = true;
+	queue[tail++] = home_value;
+	while (head < tail) {
+		const int v = queue[head++];
+		for (int a = 0; a < 12; ++a) {
+			const int v2 = t.lut[a][kind][v];
+			uint8_t moved[K];
+			for (int k = 0; k < K; ++k) {
+				int to = -1;
+				for (int x = 0; x < 48; ++x) if (t.perm686[a][x] == dst[v][k]) to = x;     // new[x] = old[perm[x]]
+				if (to < 0) return false;
+				moved[k] = (uint8_t)to;
+			}
+			if (!seen[v2]) {
+				seen[v2] = true;
+				for (int k = 0; k < K; ++k) dst[v2][k] = moved[k];
+				queue[tail++] = v2;
+			} else {
+				for (int k = 0; k < K; ++k) if (dst[v2][k] != moved[k]) return false;
+			}
+		}
+	}
+	return tail == 24;
+}
+
+static void build_stickers(Tables& t) {
+	t.stickers_ok = false;
+	int moved_by[48] = {};                                   // bitmask of faces whose turn moves the slot
+	for (int f = 0; f < 6; ++f)
+		for (int x = 0; x < 48; ++x) if (t.perm686[2 * f][x] != x) moved_by[x] |= 1 << f;
+	// corner position p: its three facelets are the slots moved by exactly the three faces that move the position; the
+	// 20x24 orientation is the axis (F/B, T/D, L/R) the tracked sticker faces (maps.py:128), so sticker k sits on axis k at home
+	uint8_t corner_slot[8][3];
+	for (int p = 0; p < 8; ++p) {
+		int faces = 0, found = 0;
+		for (int f = 0; f < 6; ++f) if (t.lut[2 * f][0][3 * p] != 3 * p) faces |= 1 << f;
+		for (int x = 0; x < 48; ++x) if (moved_by[x] == faces) { corner_slot[p][(x / 8) / 2] = (uint8_t)x; ++found; }
+		if (found != 3) return;
+	}
+	for (int c = 0; c < 8; ++c) {
+		for (int k = 0; k < 3; ++k) t.corner_home[c][k] = corner_slot[c][k];
+		if (!follow_cubie<3>(t, 0, 3 * c, t.corner_home[c], t.corner_dst[c])) return;
+		for (int v = 0; v < 24; ++v) if (t.corner_dst[c][v][0] != corner_slot[v / 3][v % 3]) return;   // tracked sticker on axis o
+	}
+	// edges: which of the two facelets carries the tracked sticker is fixed up to one global swap that the gather does not see;
+	// cubie 0 defines it for every (position, orientation), the other cubies must agree
+	uint8_t edge_slot[12][2];
+	for (int p = 0; p < 12; ++p) {
+		int faces = 0, found = 0;
+		for (int f = 0; f < 6; ++f) if (t.lut[2 * f][1][2 * p] != 2 * p) faces |= 1 << f;
+		for (int x = 0; x < 48; ++x) if (moved_by[x] == faces) { if (found < 2) edge_slot[p][found] = (uint8_t)x; ++found; }
+		if (found != 2) return;
+	}
+	t.edge_home[0][0] = edge_slot[0][0];
+	t.edge_home[0][1] = edge_slot[0][1];
+	if (!follow_cubie<2>(t, 1, 0, t.edge_home[0], t.edge_dst[0])) return;
+	for (int e = 1; e < 12; ++e) {
+		t.edge_home[e][0] = t.edge_dst[0][2 * e][0];
+		t.edge_home[e][1] = t.edge_dst[0][2 * e][1];
+		if (!follow_cubie<2>(t, 1, 2 * e, t.edge_home[e], t.edge_dst[e])) return;
+		for (int v = 0; v < 24; ++v) if (t.edge_dst[e][v][0] != t.edge_dst[0][v][0]) return;
+	}
+	t.stickers_ok = true;
+}
+
 static const Tables& host() {
 	static Tables t;
 	static std::once_flag once;
-	std::call_once(once, [] { build(t); });
+	std::call_once(once, [] { build(t); build_stickers(t); });
 	return t;
 }
 
@@ -97,6 +176,17 @@ static int ensure_device() {
 	RB_CUDA(cudaMemcpyToSymbol(g_perm686, t.perm686, sizeof(t.perm686)));
 	RB_CUDA(cudaMemcpyToSymbol(g_solved2024, t.solved2024, sizeof(t.solved2024)));
 	RB_CUDA(cudaMemcpyToSymbol(g_solved686, t.solved686, sizeof(t.solved686)));
+	{
+		// sticker tables, flat: [cubie 0..19][value 0..23][k 0..2] destination slots, [cubie][k] home slots (k = 2 unused for edges)
+		static uint8_t dst[20 * 24 * 3 + 20 * 3 + 4];
+		for (int c = 0; c < 20; ++c)
+			for (int k = 0; k < 3; ++k) {
+				const bool corner = c < 8, used = corner || k < 2;
+				dst[20 * 24 * 3 + c * 3 + k] = used ? (corner ? t.corner_home[c][k] : t.edge_home[c - 8][k]) : 0;
+				for (int v = 0; v < 24; ++v) dst[(c * 24 + v) * 3 + k] = used ? (corner ? t.corner_dst[c][v][k] : t.edge_dst[c - 8][v][k]) : 0;
+			}
+		RB_CUDA(cudaMemcpyToSymbol(g_stickers686, dst, sizeof(dst)));
+	}
 	done[dev] = true;
 	return RB_OK;
 }

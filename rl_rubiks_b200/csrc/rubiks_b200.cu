@@ -46,6 +46,16 @@ int rb_get_macro_table(uint32_t* rows) {
 	memcpy(rows, h.rows, sizeof(uint32_t) * rbs::kRows * rbs::kRowWords);
 	return RB_OK;
 }
+int rb_get_stickers686(uint8_t* corner_home, uint8_t* corner_dst, uint8_t* edge_home, uint8_t* edge_dst) {
+	RB_REQUIRE(corner_home && corner_dst && edge_home && edge_dst, "null output");
+	const rbt::Tables& t = rbt::host();
+	if (!t.stickers_ok) return rb_fail(RB_ERR_BAD_ARG, "sticker tables: the 20x24 and 6x8x6 move tables disagree%s%s");
+	memcpy(corner_home, t.corner_home, sizeof(t.corner_home));
+	memcpy(corner_dst, t.corner_dst, sizeof(t.corner_dst));
+	memcpy(edge_home, t.edge_home, sizeof(t.edge_home));
+	memcpy(edge_dst, t.edge_dst, sizeof(t.edge_dst));
+	return RB_OK;
+}
 int rb_get_solved(int rep, int8_t* state) {
 	RB_REQUIRE(state && rep_ok(rep), "bad argument");
 	if (rep == RB_REP_2024) memcpy(state, rbt::host().solved2024, 20);
@@ -162,6 +172,16 @@ int rb_scramble(int rep, const uint8_t* actions, int64_t stride_cube, int64_t st
 		RB_LAUNCHED("scramble_2024");
 	} else {
 		RB_REQUIRE(aligned(out, 16) && aligned(start, 16), "6x8x6 states must be 16-byte aligned");
+		if (depth > 0 && stride_move == 1 && stride_cube == depth && aligned(actions, 16) && rbs::warps_for(n, depth) > 0 &&
+		    rbt::host().stickers_ok && start != out) {
+			// net permutation of the sequence on the slot-major macro-move kernel (20x24 state parked at the head of each
+			// output row), then one gather of the start state's sticker records through it
+			int rc = rbs::launch(actions, out, n, depth, S(stream), rb686::kStateBytes);
+			if (rc != RB_OK) return rc;
+			rb686::k_render_from2024<<<rb_grid(n, rb686::kWarps, 8), rb686::kThreads, 0, S(stream)>>>(out, start, n);
+			RB_LAUNCHED("render_686");
+			return RB_OK;
+		}
 		rb686::k_scramble<<<rb_grid(n, rb686::kWarps, 6), rb686::kThreads, 0, S(stream)>>>(
 			actions, stride_cube, stride_move, start, out, n, depth);
 		RB_LAUNCHED("scramble_686");

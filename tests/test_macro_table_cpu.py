@@ -87,3 +87,47 @@ def test_macro_table_rows_are_permutations():
 	ident = rows[12 + 13 * 12]
 	assert ident[0] == 0x76543210 and ident[4] == 0
 	assert ((rows[:, 4] & 0x80808080) == 0).all()                                   # bit 7 of every twist|flip byte unused
+
+
+def test_sticker_tables_render_686_from_2024():
+	"""The fast 6x8x6 scramble renders the 6x8x6 state from the 20x24 state of the same move sequence through the sticker
+	tables the library derives (csrc/rb_tables.cuh build_stickers).  Emulated here in numpy against the 6x8x6 oracle, from
+	solved and from arbitrary start states."""
+	from rl_rubiks_b200 import _native as N
+	ch, cd = np.empty((8, 3), np.uint8), np.empty((8, 24, 3), np.uint8)
+	eh, ed = np.empty((12, 2), np.uint8), np.empty((12, 24, 2), np.uint8)
+	N.check(N.lib.rb_get_stickers686(ch.ctypes.data, cd.ctypes.data, eh.ctypes.data, ed.ctypes.data))
+	assert sorted(ch.ravel().tolist() + eh.ravel().tolist()) == list(range(48))          # every sticker slot exactly once
+	g = np.random.RandomState(3)
+	n, depth = 200, 37
+	faces, dirs = g.randint(0, 6, (n, depth)), g.randint(0, 2, (n, depth))
+	s2024 = O.scramble_many(faces, dirs, True)
+	start = O.scramble_many(g.randint(0, 6, (n, 11)), g.randint(0, 2, (n, 11)), False).reshape(n, 48, 6)
+	start[0] = g.randint(-5, 6, (48, 6))                                                # arbitrary int8 content is carried too
+	want = start.copy()
+	for m in range(depth):
+		want = O.multi_rotate_686(want.reshape(n, 6, 8, 6), faces[:, m], dirs[:, m]).reshape(n, 48, 6)
+	out = np.zeros_like(start)
+	rows = np.arange(n)
+	for c in range(8):
+		for k in range(3):
+			out[rows, cd[c, s2024[:, c], k]] = start[rows, ch[c, k]]
+	for e in range(12):
+		for k in range(2):
+			out[rows, ed[e, s2024[:, 8 + e], k]] = start[rows, eh[e, k]]
+	assert (out == want).all()
+	assert (O.scramble_many(faces, dirs, False).reshape(n, 48, 6) == _render_solved(ch, cd, eh, ed, s2024)).all()
+
+
+def _render_solved(ch, cd, eh, ed, s2024):
+	n = len(s2024)
+	out = np.zeros((n, 48, 6), np.int8)
+	rows = np.arange(n)
+	eye = np.eye(6, dtype=np.int8)
+	for c in range(8):
+		for k in range(3):
+			out[rows, cd[c, s2024[:, c], k]] = eye[ch[c, k] // 8]
+	for e in range(12):
+		for k in range(2):
+			out[rows, ed[e, s2024[:, 8 + e], k]] = eye[eh[e, k] // 8]
+	return out
