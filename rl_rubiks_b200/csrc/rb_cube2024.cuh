@@ -599,4 +599,40 @@ k_sequence_states(const uint8_t* __restrict__ faces, const uint8_t* __restrict__
 	}
 }
 
+// ---------------------------------------------------------------------------------------------
+// compose: states[i] <- "start[i], then the move sequence whose from-solved result is states[i]".  A sequence maps
+// (position, orientation) pairs; its from-solved state lists the images of (p, 0) for every home position p, and
+// orientation is additive in the twist / flip labelling of rb_scramble_macro.cuh, so the image of cubie value 3p+o is
+// position p' = seq[p] / 3 with twist(p', seq[p] % 3) + twist(p, o).  This lets a scramble from arbitrary start
+// states use the macro-move kernel.  Warp per state, lane = cubie, in place over `states`.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t twist_of(uint32_t pos, uint32_t ori) {
+	const bool neg = (0xa5u >> pos) & 1u;                 // positions 0, 2, 5, 7
+	return neg ? (ori ? 3u - ori : 0u) : ori;
+}
+__global__ void __launch_bounds__(kThreads)
+k_compose(int8_t* __restrict__ states, const int8_t* __restrict__ start, int64_t n) {
+	const int lane = threadIdx.x & 31;
+	const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+	const int64_t n_warps = (int64_t)gridDim.x * (kThreads / 32);
+	for (int64_t i = warp; i < n; i += n_warps) {
+		const uint32_t seq = warp_load_state(states + i * 20, lane);      // lane p < 8: image of corner position p; lane 8+p: of edge position p
+		const uint32_t s = warp_load_state(start + i * 20, lane) & 31u;
+		const bool corner = lane < 8;
+		const uint32_t p = corner ? (s * 11u) >> 5 : s >> 1;               // s / 3 for s < 32
+		const uint32_t o = corner ? s - 3u * p : s & 1u;
+		const uint32_t img = __shfl_sync(0xffffffffu, seq, corner ? min(p, 7u) : 8u + min(p, 11u)) & 31u;
+		uint32_t out;
+		if (corner) {
+			const uint32_t p2 = (img * 11u) >> 5, o2 = img - 3u * p2;
+			uint32_t t = twist_of(p2 & 7u, o2) + twist_of(p & 7u, o);
+			t = t >= 3u ? t - 3u : t;
+			out = 3u * p2 + twist_of(p2 & 7u, t);                          // twist <-> orientation is an involution per position
+		} else {
+			out = img ^ o;
+		}
+		if (lane < 20) states[i * 20 + lane] = (int8_t)out;
+	}
+}
+
 }  // namespace rb2024

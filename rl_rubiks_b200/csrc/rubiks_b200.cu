@@ -165,8 +165,13 @@ int rb_scramble(int rep, const uint8_t* actions, int64_t stride_cube, int64_t st
 	RB_REQUIRE(out && (actions || depth == 0), "null pointer");
 	RB_INIT();
 	if (rep == RB_REP_2024) {
-		if (!start && depth > 0 && stride_move == 1 && stride_cube == depth && aligned(actions, 16) && rbs::warps_for(n, depth) > 0)
-			return rbs::launch(actions, out, n, depth, S(stream));      // slot-major macro-move kernel (cube-major actions)
+		if (depth > 0 && stride_move == 1 && stride_cube == depth && aligned(actions, 16) && rbs::warps_for(n, depth) > 0 && start != out) {
+			int rc = rbs::launch(actions, out, n, depth, S(stream));    // slot-major macro-move kernel (cube-major actions)
+			if (rc != RB_OK || !start) return rc;
+			rb2024::k_compose<<<rb_grid(n, 8, 8), rb2024::kThreads, 0, S(stream)>>>(out, start, n);   // start, then the sequence
+			RB_LAUNCHED("compose_2024");
+			return RB_OK;
+		}
 		rb2024::k_scramble<<<rb_grid(n, rb2024::kThreads, 8), rb2024::kThreads, 0, S(stream)>>>(
 			actions, stride_cube, stride_move, start, out, n, depth);
 		RB_LAUNCHED("scramble_2024");
