@@ -27,7 +27,12 @@ torch.cuda.set_device(dev)
 FLUSH = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
+ONCE = False       # --once: a single launch per kernel (for ncu captures)
+
+
 def timeit(fn, reps=7, warm=2):
+	if ONCE:
+		reps, warm = 1, 0
 	for _ in range(warm):
 		fn()
 	ms = []
@@ -69,7 +74,10 @@ def main():
 	ap = argparse.ArgumentParser()
 	ap.add_argument("--quick", action="store_true")
 	ap.add_argument("--only", default="")
+	ap.add_argument("--once", action="store_true", help="one launch per kernel, no warm-up (use under ncu)")
 	args = ap.parse_args()
+	global ONCE
+	ONCE = args.once
 	sh = N.stream_handle()
 	q = 4 if args.quick else 1
 	want = lambda name: args.only in name
