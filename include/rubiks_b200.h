@@ -168,6 +168,41 @@ int rb_frontier_expand(int rep, void* table, int64_t capacity, const int8_t* fro
                        void* scratch, rb_stream_t stream);
 int64_t rb_frontier_scratch_bytes(int rep, int64_t n);
 
+/* ---- batched weighted A* on the device (agents.py:221-367 for K cubes at once; 20x24 representation) -----------------
+ * K independent searches advance in lockstep.  Every buffer is caller-owned device memory; [K][M] arrays are indexed by the
+ * reference's state index (1-based, 0 unused), M >= max_states + 1.  One step of all searches =
+ *   rb_astar_expand  (pop the <= N cheapest open states per search in heapq order, expand, dedup, number and store the new
+ *                     states, append them to one contiguous batch for the value net)
+ *   [caller: one-hot + value net on new_states[0 .. *n_new_total)]
+ *   rb_astar_commit  (costs lambda*G - value into the open list, the two relaxation passes, bookkeeping).
+ * A search stops when it generated the solved state (won[s] = 1, solved_index[s]) or when count[s] + 12 N > max_states. */
+typedef struct rb_astar_view {
+	int32_t K, M, N;              /* searches, rows per search, expansions per step (N <= 1024) */
+	int8_t*  states;              /* [K][M][20] */
+	double*  G;                   /* [K][M] path cost upper bound */
+	int32_t* parents;             /* [K][M] */
+	uint8_t* parent_actions;      /* [K][M] */
+	double*  cost;                /* [K][M] the (cost, index) heap entry of a state, valid while in_open */
+	uint8_t* in_open;             /* [K][M] */
+	int32_t* count;               /* [K] states stored (= len(agent)) */
+	int32_t* n_sel;               /* [K] parents popped in the running step */
+	int32_t* sel;                 /* [K][N] their indices, ascending (cost, index) */
+	uint8_t* won;                 /* [K] */
+	int32_t* solved_index;        /* [K] */
+	void*    table;               /* shared seen-set, rb_hashset_bytes(capacity) bytes, cleared with rb_hashset_clear */
+	int64_t  capacity;            /* power of two, >= 2 K M */
+	void*    scratch;             /* rb_astar_scratch_bytes(K, N) bytes */
+} rb_astar_view;
+int64_t rb_astar_scratch_bytes(int32_t K, int32_t N);
+/* roots int8 [K][20]: state 1 of every search (a solved root marks the search won at once, agents.py:230). */
+int rb_astar_init(const rb_astar_view* v, const int8_t* roots, rb_stream_t stream);
+/* new_states int8 [K*12N][20], new_search / new_index int32 [K*12N]; n_new_total, n_active: int32 on the device. */
+int rb_astar_expand(const rb_astar_view* v, int64_t max_states, int8_t* new_states, int32_t* new_search,
+                    int32_t* new_index, int32_t* n_new_total, int32_t* n_active, rb_stream_t stream);
+/* values f32 [*n_new_total]: the value net's output for new_states, in order. */
+int rb_astar_commit(const rb_astar_view* v, const float* values, double lambda, const int32_t* new_search,
+                    const int32_t* new_index, const int32_t* n_new_total, rb_stream_t stream);
+
 /* ---- host-buffer entry points (end-to-end: H2D + kernels + D2H inside the call) --------------- */
 /* rb_scramble on host buffers; actions uint8 [n][depth] (cube-major), out int8 [n][*shape].  Copies are
  * chunked and double-buffered on internal streams; pinned host memory makes them asynchronous. */

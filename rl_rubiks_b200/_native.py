@@ -55,6 +55,10 @@ SIGNATURES = {
 	"rb_hashset_lookup": (C.c_int, [C.c_int, _p, _i64, _p, _i64, _p, _p, _p]),
 	"rb_frontier_expand": (C.c_int, [C.c_int, _p, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
 	"rb_frontier_scratch_bytes": (_i64, [C.c_int, _i64]),
+	"rb_astar_scratch_bytes": (_i64, [_i32, _i32]),
+	"rb_astar_init": (C.c_int, [_p, _p, _p]),
+	"rb_astar_expand": (C.c_int, [_p, _i64, _p, _p, _p, _p, _p, _p]),
+	"rb_astar_commit": (C.c_int, [_p, _p, _f64, _p, _p, _p, _p]),
 	"rbh_scramble": (C.c_int, [C.c_int, _p, _p, _i64, _i32]),
 	"rbh_multi_rotate": (C.c_int, [C.c_int, _p, _p, _p, _p, _i64]),
 	"rbh_release": (C.c_int, []),
@@ -63,6 +67,13 @@ SIGNATURES = {
 for _name, (_res, _args) in SIGNATURES.items():
 	_fn = getattr(lib, _name)          # AttributeError here = the .so does not match the header
 	_fn.restype, _fn.argtypes = _res, _args
+
+
+class AStarView(C.Structure):
+	"""rb_astar_view (include/rubiks_b200.h)."""
+	_fields_ = [("K", _i32), ("M", _i32), ("N", _i32), ("states", _p), ("G", _p), ("parents", _p), ("parent_actions", _p),
+				("cost", _p), ("in_open", _p), ("count", _p), ("n_sel", _p), ("sel", _p), ("won", _p), ("solved_index", _p),
+				("table", _p), ("capacity", _i64), ("scratch", _p)]
 
 
 class RubiksError(RuntimeError):

@@ -6,6 +6,7 @@
 #include "rb_cube686.cuh"
 #include "rb_adi.cuh"
 #include "rb_frontier.cuh"
+#include "rb_astar.cuh"
 #include "rb_host.cuh"
 
 #define RB_INIT()                                   \
@@ -459,6 +460,96 @@ int rb_check_range(int rep, const int8_t* states, int64_t n_states, const uint8_
 	RB_CUDA(cudaMemcpyAsync(&flag, scratch_dev, sizeof(flag), cudaMemcpyDeviceToHost, S(stream)));
 	RB_CUDA(cudaStreamSynchronize(S(stream)));
 	if (flag) return rb_fail(RB_ERR_RANGE, "index out of range: face >= 6, direction >= 2, action >= 12 or state value >= 24%s%s");
+	return RB_OK;
+}
+
+// ---- batched A* ----------------------------------------------------------------------------------------------------------
+static inline int64_t up16(int64_t x) { return (x + 15) / 16 * 16; }
+
+int64_t rb_astar_scratch_bytes(int32_t K, int32_t N) {
+	if (K <= 0 || N <= 0) return 0;
+	const int64_t P = 12 * (int64_t)N, nbx = (P + rba::kThreads - 1) / rba::kThreads;
+	return up16(K * P * 4) + up16(K * P) + up16(K * P * 8) + up16(K * nbx * 4) + up16((int64_t)K * 4) + up16((int64_t)(K + 1) * 4) + 64;
+}
+
+static int astar_view(const rb_astar_view* a, rba::View& v) {
+	RB_REQUIRE(a, "null view");
+	RB_REQUIRE(a->K > 0 && a->K <= 65535 && a->M > 1 && a->N > 0 && a->N <= 1024, "bad K / M / N (K <= 65535, N <= 1024)");
+	RB_REQUIRE(a->states && a->G && a->parents && a->parent_actions && a->cost && a->in_open && a->count && a->n_sel && a->sel && a->won &&
+	           a->solved_index && a->table && a->scratch, "null buffer in view");
+	RB_REQUIRE(pow2(a->capacity) && aligned(a->table, 16) && aligned(a->scratch, 16) && aligned(a->states, 4) && aligned(a->G, 8) && aligned(a->cost, 8),
+	           "misaligned buffer or capacity not a power of two");
+	const int64_t K = a->K, P = 12 * (int64_t)a->N, nbx = (P + rba::kThreads - 1) / rba::kThreads;
+	v.K = a->K; v.M = a->M; v.N = a->N;
+	v.states = a->states; v.G = a->G; v.parents = a->parents; v.parent_actions = a->parent_actions; v.cost = a->cost; v.in_open = a->in_open;
+	v.count = a->count; v.n_sel = a->n_sel; v.sel = a->sel; v.won = a->won; v.solved_index = a->solved_index;
+	v.table = a->table; v.capacity = a->capacity;
+	uint8_t* p = reinterpret_cast<uint8_t*>(a->scratch);
+	v.slot = reinterpret_cast<int32_t*>(p); p += up16(K * P * 4);
+	v.flags = p; p += up16(K * P);
+	v.tmp = reinterpret_cast<double*>(p); p += up16(K * P * 8);
+	v.block_new = reinterpret_cast<int32_t*>(p); p += up16(K * nbx * 4);
+	v.n_new = reinterpret_cast<int32_t*>(p); p += up16(K * 4);
+	v.off = reinterpret_cast<int32_t*>(p);
+	return RB_OK;
+}
+
+int rb_astar_init(const rb_astar_view* a, const int8_t* roots, rb_stream_t stream) {
+	rba::View v;
+	int rc = astar_view(a, v);
+	if (rc != RB_OK) return rc;
+	RB_REQUIRE(roots && aligned(roots, 4), "roots must be a 4-byte aligned device pointer");
+	RB_INIT();
+	rba::k_init<<<(v.K + rba::kThreads - 1) / rba::kThreads, rba::kThreads, 0, S(stream)>>>(v, roots);
+	RB_LAUNCHED("astar_init");
+	return RB_OK;
+}
+
+int rb_astar_expand(const rb_astar_view* a, int64_t max_states, int8_t* new_states, int32_t* new_search, int32_t* new_index,
+                    int32_t* n_new_total, int32_t* n_active, rb_stream_t stream) {
+	rba::View v;
+	int rc = astar_view(a, v);
+	if (rc != RB_OK) return rc;
+	RB_REQUIRE(new_states && new_search && new_index && n_new_total && n_active && aligned(new_states, 4), "null or misaligned output");
+	RB_REQUIRE(max_states < v.M, "M must exceed max_states (index 0 is unused)");
+	RB_INIT();
+	cudaStream_t st = S(stream);
+	const dim3 grid(v.nbx(), v.K);
+	RB_CUDA(cudaMemsetAsync(n_active, 0, sizeof(int32_t), st));
+	rba::k_select<<<v.K, rba::kSelThreads, 0, st>>>(v, max_states, n_active);
+	RB_LAUNCHED("astar_select");
+	rba::k_probe<<<grid, rba::kThreads, 0, st>>>(v);
+	RB_LAUNCHED("astar_probe");
+	rba::k_flag<<<grid, rba::kThreads, 0, st>>>(v);
+	RB_LAUNCHED("astar_flag");
+	rba::k_totals<<<1, 1024, 0, st>>>(v, n_new_total);
+	RB_LAUNCHED("astar_totals");
+	rba::k_assign<<<grid, rba::kThreads, 0, st>>>(v, new_states, new_search, new_index);
+	RB_LAUNCHED("astar_assign");
+	return RB_OK;
+}
+
+int rb_astar_commit(const rb_astar_view* a, const float* values, double lambda, const int32_t* new_search, const int32_t* new_index,
+                    const int32_t* n_new_total, rb_stream_t stream) {
+	rba::View v;
+	int rc = astar_view(a, v);
+	if (rc != RB_OK) return rc;
+	RB_REQUIRE(values && new_search && new_index && n_new_total, "null input");
+	cudaStream_t st = S(stream);
+	const dim3 grid(v.nbx(), v.K);
+	const int64_t worst = (int64_t)v.K * v.P();
+	rba::k_push<<<(unsigned)((worst + rba::kThreads - 1) / rba::kThreads), rba::kThreads, 0, st>>>(v, values, lambda, new_search, new_index, n_new_total);
+	RB_LAUNCHED("astar_push");
+	rba::k_relax_eval<<<grid, rba::kThreads, 0, st>>>(v, 0);
+	RB_LAUNCHED("astar_relax_eval0");
+	rba::k_relax_new_ways<<<grid, rba::kThreads, 0, st>>>(v);
+	RB_LAUNCHED("astar_relax_new_ways");
+	rba::k_relax_eval<<<grid, rba::kThreads, 0, st>>>(v, 1);
+	RB_LAUNCHED("astar_relax_eval1");
+	rba::k_relax_shortcuts<<<dim3((v.N + rba::kThreads - 1) / rba::kThreads, v.K), rba::kThreads, 0, st>>>(v);
+	RB_LAUNCHED("astar_relax_shortcuts");
+	rba::k_finish<<<grid, rba::kThreads, 0, st>>>(v);
+	RB_LAUNCHED("astar_finish");
 	return RB_OK;
 }
 

@@ -480,3 +480,98 @@ class MCTS(Agent):
 
 	def __str__(self):
 		return ("BFS" if self.search_graph else "Naive") + f" MCTS (c={self.c})"
+
+
+class AStarBatch:
+	"""Batched weighted A* (agents.py:171-413) for K cubes at once, entirely on the device (SURVEY 8f rows N2 + N3): open
+	list, seen-set, G / parent relaxation and the pop of the N cheapest states per search are kernels (csrc/rb_astar.cuh);
+	the host only runs the value net on the contiguous batch of new states of all searches and reads two counters per step.
+	Every search follows the reference's trace exactly (same pops, same state numbering, same G / parents / action queue).
+	20x24 representation."""
+
+	def __init__(self, net, lambda_: float, expansions: int):
+		N.require_cuda()
+		if not 0 < expansions <= 1024:
+			raise ValueError("expansions must be in 1..1024")
+		self.net, self.lambda_, self.expansions = net, float(lambda_), int(expansions)
+		self.dev = torch.device("cuda", torch.cuda.current_device())
+
+	def _alloc(self, K: int, max_states: int):
+		dev, Nx = self.dev, self.expansions
+		M = max_states + 1
+		self.K, self.M = K, M
+		self.states = torch.empty(K, M, 20, dtype=torch.int8, device=dev)
+		self.G = torch.empty(K, M, dtype=torch.float64, device=dev)
+		self.parents = torch.zeros(K, M, dtype=torch.int32, device=dev)
+		self.parent_actions = torch.zeros(K, M, dtype=torch.uint8, device=dev)
+		self.cost = torch.empty(K, M, dtype=torch.float64, device=dev)
+		self.in_open = torch.zeros(K, M, dtype=torch.uint8, device=dev)
+		self.count = torch.zeros(K, dtype=torch.int32, device=dev)
+		self.n_sel = torch.zeros(K, dtype=torch.int32, device=dev)
+		self.sel = torch.zeros(K, Nx, dtype=torch.int32, device=dev)
+		self.won = torch.zeros(K, dtype=torch.uint8, device=dev)
+		self.solved_index = torch.zeros(K, dtype=torch.int32, device=dev)
+		self.capacity = _pow2_at_least(2 * K * M)
+		self.table = torch.empty(N.lib.rb_hashset_bytes(self.capacity), dtype=torch.uint8, device=dev)
+		self.scratch = torch.empty(N.lib.rb_astar_scratch_bytes(K, Nx), dtype=torch.uint8, device=dev)
+		P = 12 * Nx
+		self.new_states = torch.empty(K * P, 20, dtype=torch.int8, device=dev)
+		self.new_search = torch.empty(K * P, dtype=torch.int32, device=dev)
+		self.new_index = torch.empty(K * P, dtype=torch.int32, device=dev)
+		self.counters = torch.zeros(2, dtype=torch.int32, device=dev)          # n_new_total, n_active
+		self.oh = torch.empty(K * P, 480, dtype=torch.float32, device=dev)
+		self.view = N.AStarView(K, M, Nx, *(N.ptr(t) for t in (self.states, self.G, self.parents, self.parent_actions, self.cost, self.in_open,
+																 self.count, self.n_sel, self.sel, self.won, self.solved_index, self.table)),
+								self.capacity, N.ptr(self.scratch))
+
+	@torch.no_grad()
+	def search_many(self, states, max_states: int, max_steps: int | None = None):
+		"""states: (K, 20) int8 (numpy or CUDA tensor).  Returns (solved bool (K,), action queues: list of K lists,
+		len per search int (K,)), the three things `AStar.search` leaves behind for one cube."""
+		import ctypes as C
+		s = states if isinstance(states, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(states, dtype=np.int8))
+		roots = s.to(device=self.dev, dtype=torch.int8).reshape(-1, 20).contiguous()
+		self._alloc(roots.shape[0], int(max_states))
+		self.net.eval()
+		sh = N.stream_handle()
+		v = C.byref(self.view)
+		N.check(N.lib.rb_hashset_clear(N.ptr(self.table), self.capacity, sh))
+		N.check(N.lib.rb_astar_init(v, N.ptr(roots), sh))
+		n_total_ptr, n_active_ptr = C.c_void_p(self.counters.data_ptr()), C.c_void_p(self.counters.data_ptr() + 4)
+		self.steps = 0
+		while max_steps is None or self.steps < max_steps:
+			N.check(N.lib.rb_astar_expand(v, int(max_states), N.ptr(self.new_states), N.ptr(self.new_search), N.ptr(self.new_index),
+										  n_total_ptr, n_active_ptr, sh))
+			n_total, n_active = (int(x) for x in self.counters.tolist())         # the one host sync of a step
+			if n_active == 0:
+				break
+			values = self._values(n_total)
+			N.check(N.lib.rb_astar_commit(v, N.ptr(values), self.lambda_, N.ptr(self.new_search), N.ptr(self.new_index), n_total_ptr, sh))
+			self.steps += 1
+		return self._results()
+
+	def _values(self, n: int) -> torch.Tensor:
+		"""agents.py:379-381: one-hot born on the device, value head only; f32 (n,)."""
+		if n == 0:
+			return torch.zeros(1, dtype=torch.float32, device=self.dev)
+		oh = self.oh[:n]
+		N.check(N.lib.rb_as_oh(N.REP_2024, N.ptr(self.new_states), N.ptr(oh), n, N.stream_handle()))
+		val = self.net(oh, value=True, policy=False)
+		return val.reshape(-1).float().contiguous()
+
+	def _results(self):
+		won = self.won.bool().cpu().numpy()
+		count = self.count.cpu().numpy().astype(int)
+		solved_index = self.solved_index.cpu().numpy()
+		queues = []
+		for s in range(self.K):
+			q = []
+			if won[s] and solved_index[s] > 1:
+				n = count[s] + 1
+				parents, actions = self.parents[s, :n].cpu().numpy(), self.parent_actions[s, :n].cpu().numpy()
+				i = int(solved_index[s])
+				while i != 1:                                            # agents.py:245-251
+					q.insert(0, int(actions[i]))
+					i = int(parents[i])
+			queues.append(q)
+		return won, queues, count

@@ -212,3 +212,56 @@ def test_mcts_686_solves_shallow_scramble():
 	for act in m.action_queue:
 		s = cube.rotate(s, *cube.action_space[act])
 	assert cube.is_solved(s) and len(m) == len(m.hs)
+
+
+def _oracle_astar(start, lam, n_exp, w, max_states, quant=4.0):
+	"""AStar.search (agents.py:221-252) on the oracle's bookkeeping with the integer fake net."""
+	h = lambda states: -np.floor((O.as_oh_2024(states) @ w) / np.float32(quant)).astype(np.float32)
+	a = O.AStarFrontier(lam, n_exp, h)
+	a.reset(start, capacity=max_states + 12 * n_exp + 2)
+	if O.is_solved(start, True):
+		return True, a
+	while len(a) + 12 * n_exp <= max_states:
+		won, _ = a.expand_batch(a.pop_batch())
+		if won:
+			return True, a
+	return False, a
+
+
+@pytest.mark.parametrize("n_exp,max_states,lam", [(7, 700, 0.16), (64, 5000, 0.5), (700, 30000, 0.16)])
+def test_astar_batch_matches_single_search_traces(golden, n_exp, max_states, lam):
+	"""AStarBatch (device open list, pops, dedup, relaxation for K cubes in lockstep) against the single-search bookkeeping
+	of the reference, search by search: solved flag, len, stored states, G, parents, parent actions, open list, action queue."""
+	from rl_rubiks_b200 import cube
+	from rl_rubiks_b200.frontier import AStarBatch
+	g = golden("search")
+	w = g["astar_w_2024"]
+	rng = np.random.RandomState(n_exp)
+	starts = [g["astar_start_2024"], O.solved_2024()]
+	for depth in (1, 2, 3, 4, 5, 6, 8, 11, 30):
+		starts.append(O.scramble(rng.randint(0, 6, depth), rng.randint(0, 2, depth), True))
+	starts = np.stack(starts)
+	agent = AStarBatch(_FakeNet(w), lambda_=lam, expansions=n_exp)
+	won, queues, count = agent.search_many(starts, max_states)
+	for s, start in enumerate(starts):
+		ok, a = _oracle_astar(start, lam, n_exp, w, max_states)
+		L = len(a)
+		assert bool(won[s]) == ok and count[s] == L, (s, won[s], ok, count[s], L)
+		assert (agent.states[s, 1:L + 1].cpu().numpy() == a.states[1:L + 1]).all()
+		assert (agent.G[s, 1:L + 1].cpu().numpy() == a.G[1:L + 1]).all()
+		assert (agent.parents[s, 2:L + 1].cpu().numpy() == a.parents[2:L + 1]).all()
+		assert (agent.parent_actions[s, 2:L + 1].cpu().numpy() == a.parent_actions[2:L + 1]).all()
+		if not ok or L == 1:
+			in_open = agent.in_open[s, :L + 1].bool().cpu().numpy()
+			cost = agent.cost[s, :L + 1].cpu().numpy()
+			mine = sorted((float(cost[i]), int(i)) for i in np.where(in_open)[0])
+			assert mine == sorted((float(c), int(i)) for c, i in a.open) or L == 1
+		if ok:
+			state = start
+			for act in queues[s]:
+				state = cube.rotate(state, *cube.action_space[act])
+			assert cube.is_solved(state)
+			i, q = int(a.seen.lookup(O.solved_2024()[None])[0]), []
+			while i != 1:
+				q.insert(0, int(a.parent_actions[i])); i = int(a.parents[i])
+			assert q == queues[s]
