@@ -64,6 +64,8 @@ int rb_get_perm686(uint8_t* perm);
 /* The fused 2-move table of the fast scramble kernel (csrc/rb_scramble_macro.cuh): uint32[13*13][5], row index
  * a0 + 13 a1 (action 12 = identity), derived from the 20x24 LUT.  For inspection / CPU emulation tests. */
 int rb_get_macro_table(uint32_t* rows);
+/* The fused 3-move table of the same kernel's 3-moves-per-row variant: uint32[12*12*12][5], row index a0 + 12 a1 + 144 a2. */
+int rb_get_macro3_table(uint32_t* rows);
 /* Sticker view used to render a 6x8x6 state from the 20x24 state of the same move sequence (fast 6x8x6 scramble):
  * corner_home uint8[8][3], corner_dst uint8[8][24][3], edge_home uint8[12][2], edge_dst uint8[12][24][2]: sticker k of a
  * cubie sits in 6x8x6 slot *_home[c][k] when solved and in slot *_dst[c][v][k] when the cubie's 20x24 value is v.

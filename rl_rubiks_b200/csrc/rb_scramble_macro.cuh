@@ -43,6 +43,7 @@ constexpr int kSmemBudget = 227 * 1024;
 constexpr int kReduceEvery = 10;                // rows between twist folds (5 action words): 10 + 10 * 2 <= 31
 
 __device__ __align__(16) uint32_t g_macro[kRows * kRowWords + 3];
+__device__ __align__(16) uint32_t g_macro3[12 * 12 * 12 * kRowWords + 3];
 
 struct Elem {                                   // one cube-group element in slot-major gather form
 	uint8_t csrc[8], ctw[8], esrc[12], efl[12];
@@ -109,8 +110,11 @@ static void encode(const Elem& e, uint32_t* row) {
 	row[4] = tf;
 }
 
+constexpr int kRows3 = 12 * 12 * 12;            // 3-move rows, index a0 + 12 a1 + 144 a2 (no identity padding: the tail uses the 2-move table)
+
 struct Host {
 	uint32_t rows[kRows * kRowWords + 3];
+	uint32_t rows3[kRows3 * kRowWords + 3];
 	bool ok;
 };
 
@@ -128,6 +132,12 @@ static const Host& host() {
 				Elem x;
 				compose(s[a0], s[a1], x);
 				encode(x, h.rows + (a0 + kA * a1) * kRowWords);
+				if (a0 < 12 && a1 < 12)
+					for (int a2 = 0; a2 < 12; ++a2) {
+						Elem y;
+						compose(x, s[a2], y);
+						encode(y, h.rows3 + (a0 + 12 * a1 + 144 * a2) * kRowWords);
+					}
 			}
 	});
 	return h;
@@ -338,6 +348,199 @@ k_scramble_macro(const uint8_t* __restrict__ actions, int8_t* __restrict__ out, 
 	}
 }
 
+// ---- 3-move rows --------------------------------------------------------------------------------------------------------
+// Same state, same row format, but one row = three consecutive moves (12^3 = 1728 rows): a third fewer PRMT / LOP3 / IMAD
+// per move on the math pipes that bound the 2-move kernel.  The price is the table: 8 conflict-free copies of the 16-byte
+// part would need 221 KB, so it is kept in kRep1 = 4 copies laid out row-major [row][copy] -- copy k = lane % 4 lives in
+// bank groups {k, k + 4}, so within one quarter-warp phase of the LDS.128 only the two lanes that share a copy can collide
+// (when their rows have the same parity): ~1.9 wavefronts per phase instead of 2.6 for an unreplicated table.  The 4-byte
+// twist|flip word comes from a second array with R2 copies.  Trailing depth % 3 moves use the 2-move table (one copy).
+// Action bytes are masked to 4 bits, so an out-of-range action forms a row index <= kIdxMax3 that still lies inside the
+// CTA's shared memory (the launch always requests at least that much): an unspecified but memory-safe result.
+constexpr int kRep1 = 4;
+constexpr int kIdxMax3 = 15 + 12 * 15 + 144 * 15;           // 2355
+constexpr int kP1Bytes3 = kRows3 * kRep1 * 16;              // 110,592
+constexpr int kP2Rows3 = 2368;                              // > kIdxMax3
+constexpr int kTailBytes = kDevRows * 32;                   // 2-move rows padded to 32 bytes, one copy
+constexpr int kMinSmem3 = (kIdxMax3 + 1) * kRep1 * 16 + 128;
+
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) {
+	uint32_t o;
+	asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(o) : "r"(a), "r"(b), "r"(c));
+	return o;
+}
+
+// Shared-memory loads by 32-bit shared-space address (no generic-to-shared base add per row).
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+	uint4 v;
+	asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+	return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+	uint32_t v;
+	asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+	return v;
+}
+
+// Per byte: 5-bit twist accumulator (bits 0-4) -> its value mod 3, by base-4 digit folds (4 == 1 mod 3); other bits ignored.
+__device__ __forceinline__ uint32_t mod3_bytes(uint32_t c) {
+	uint32_t t = (c & 0x03030303u) + ((c >> 2) & 0x07070707u);       // <= 3 + 7
+	t = (t & 0x03030303u) + ((t >> 2) & 0x03030303u);                 // <= 3 + 2
+	t = (t & 0x03030303u) + ((t >> 2) & 0x01010101u);                 // 0..3, 3 == 0
+	const uint32_t x = t & (t >> 1) & 0x01010101u;
+	return t ^ (x * 3u);
+}
+
+// Slot-major -> cubie-major int8[20], four slots per step in SIMD-within-register form; only the scatter by cubie id is
+// per byte.  `o` is this cube's 20-byte output row in shared memory.
+__device__ __forceinline__ void store_state_simd(uint8_t* __restrict__ o, const Slots& s) {
+#pragma unroll
+	for (int h = 0; h < 2; ++h) {
+		const uint32_t c = h ? s.C1 : s.C0;
+		const uint32_t neg = h ? 0xff00ff00u : 0x00ff00ffu;                      // positions 0, 2, 5, 7 carry the twist negated
+		const uint32_t t = mod3_bytes(c);
+		const uint32_t sw = ((t << 1) & 0x02020202u) | ((t >> 1) & 0x01010101u);   // 1 <-> 2
+		const uint32_t v = (h ? 0x15120f0cu : 0x09060300u) + ((t & ~neg) | (sw & neg));
+		const uint32_t id = (c >> 5) & 0x07070707u;
+#pragma unroll
+		for (int i = 0; i < 4; ++i) o[(id >> (8 * i)) & 0xffu] = (uint8_t)(v >> (8 * i));
+	}
+#pragma unroll
+	for (int d = 0; d < 3; ++d) {
+		const uint32_t e = d == 0 ? s.E0 : (d == 1 ? s.E1 : s.E2);
+		const uint32_t f = ((e >> 4) ^ (e >> 5) ^ (e >> 6)) & 0x01010101u;
+		const uint32_t v = (d == 0 ? 0x06040200u : (d == 1 ? 0x0e0c0a08u : 0x16141210u)) + f;
+		const uint32_t id = e & 0x0f0f0f0fu;
+#pragma unroll
+		for (int i = 0; i < 4; ++i) o[8u + ((id >> (8 * i)) & 0xffu)] = (uint8_t)(v >> (8 * i));
+	}
+}
+
+template <bool kWordAligned, int R2>
+__global__ void __launch_bounds__(kMaxThreads, 1)
+k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out, int64_t n, int depth, int out_pitch) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	constexpr int kP2Bytes3 = kP2Rows3 * 4 * R2;
+	uint8_t* table = smem;                                              // [P1 | P2 | tail | mbarriers | action buffers]
+	uint8_t* tail = smem + kP1Bytes3 + kP2Bytes3;
+	uint64_t* bars = reinterpret_cast<uint64_t*>(tail + kTailBytes);
+	const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+	const int chunk_bytes = 32 * depth;
+	uint8_t* buf = reinterpret_cast<uint8_t*>(bars) + kMaxThreads / 32 * 8 + (size_t)wib * chunk_bytes;
+	uint64_t* bar = &bars[wib];
+	const uint32_t off1 = smem_u32(table) + (lane & (kRep1 - 1)) * 16u, off2 = smem_u32(table) + (uint32_t)kP1Bytes3 + (lane & (R2 - 1)) * 4u;
+
+	const int64_t n_chunks = (n + 31) / 32;
+	const int64_t stride = (int64_t)gridDim.x * n_warps;
+	int64_t chunk = (int64_t)blockIdx.x * n_warps + wib;
+
+	auto issue = [&](int64_t c) {
+		const int cnt = (int)min((int64_t)32, n - c * 32);
+		const uint32_t bulk = (uint32_t)(cnt * depth) & ~15u;
+		if (bulk) {
+			mbar_expect_tx(bar, bulk);
+			bulk_g2s(buf, actions + c * chunk_bytes, bulk, bar);
+		}
+	};
+	if (lane == 0) mbar_init(bar, 1);
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	__syncwarp();
+	if (lane == 0 && chunk < n_chunks) issue(chunk);
+	for (int i = threadIdx.x; i < kP2Rows3 * kRep1; i += blockDim.x) {
+		const int row = i / kRep1, c = i % kRep1;
+		if (row < kRows3) {
+			const uint32_t* r = g_macro3 + row * kRowWords;
+			*reinterpret_cast<uint4*>(table + (row * kRep1 + c) * 16) = make_uint4(r[0], r[1], r[2], r[3]);
+			if (c < R2) *reinterpret_cast<uint32_t*>(table + kP1Bytes3 + (row * R2 + c) * 4) = r[4];
+		} else if (c < R2) {
+			*reinterpret_cast<uint32_t*>(table + kP1Bytes3 + (row * R2 + c) * 4) = 0u;
+		}
+	}
+	for (int i = threadIdx.x; i < kDevRows; i += blockDim.x) {
+		const uint32_t* r = g_macro + (i < kRows ? i : kRows - 1) * kRowWords;
+		*reinterpret_cast<uint4*>(tail + i * 32) = make_uint4(r[0], r[1], r[2], r[3]);
+		*reinterpret_cast<uint32_t*>(tail + i * 32 + 16) = r[4];
+	}
+	__syncthreads();
+
+	uint32_t parity = 0;
+	for (; chunk < n_chunks; chunk += stride) {
+		const int cnt = (int)min((int64_t)32, n - chunk * 32);
+		const int bytes = cnt * depth, bulk = bytes & ~15;
+		if (bulk < bytes) {
+			if ((int)lane < bytes - bulk) buf[bulk + lane] = actions[chunk * chunk_bytes + bulk + lane];
+			__syncwarp();
+		}
+		if (bulk) { mbar_wait(bar, parity); parity ^= 1u; }
+
+		if ((int)lane < cnt) {
+			uint8_t* row = buf + lane * depth;
+			Slots s{0x60402000u, 0xe0c0a080u, 0x03020100u, 0x07060504u, 0x0b0a0908u};
+			auto word_at = [&](int m) -> uint32_t {
+				if (kWordAligned) return *reinterpret_cast<const uint32_t*>(row + m);
+				return row[m] | (row[m + 1] << 8) | (row[m + 2] << 16) | ((uint32_t)row[m + 3] << 24);
+			};
+			auto apply3 = [&](uint32_t r) {
+				const uint32_t o1 = mad_u32(r, 16u * kRep1, off1), o2 = mad_u32(r, 4u * R2, off2);
+				apply_row(lds128(o1), lds32(o2), s);
+			};
+			// 12 moves = 3 action words = 4 rows; the row index a0 + 12 a1 + 144 a2 is one or two dp4a
+			auto apply_words = [&](uint32_t w0, uint32_t w1, uint32_t w2) {
+				w0 &= 0x0f0f0f0fu; w1 &= 0x0f0f0f0fu; w2 &= 0x0f0f0f0fu;
+				apply3(__dp4a(w0, 0x00900C01u, 0u));
+				apply3(__dp4a(w0, 0x01000000u, __dp4a(w1, 0x0000900Cu, 0u)));
+				apply3(__dp4a(w1, 0x0C010000u, __dp4a(w2, 0x00000090u, 0u)));
+				apply3(__dp4a(w2, 0x900C0100u, 0u));
+			};
+			int m = 0;
+			for (; m + 24 <= depth; m += 24) {                              // 8 rows add at most 16 to a twist accumulator <= 10
+				const uint32_t w0 = word_at(m), w1 = word_at(m + 4), w2 = word_at(m + 8), w3 = word_at(m + 12), w4 = word_at(m + 16),
+				               w5 = word_at(m + 20);
+				apply_words(w0, w1, w2); apply_words(w3, w4, w5);
+				s.C0 = fold_twists(s.C0); s.C1 = fold_twists(s.C1);
+			}
+			if (m < depth) {                                                // < 24 moves left: at most 4 + 3 + 1 rows
+				if (m + 12 <= depth) { apply_words(word_at(m), word_at(m + 4), word_at(m + 8)); m += 12; }
+				for (; m + 3 <= depth; m += 3) apply3((row[m] & 15u) + 12u * (row[m + 1] & 15u) + 144u * (row[m + 2] & 15u));
+				if (m < depth) {                                            // one or two trailing moves: 2-move row, identity padded
+					const uint32_t a0 = row[m] & 15u, a1 = m + 1 < depth ? row[m + 1] & 15u : 12u;
+					const uint8_t* r = tail + (a0 + 13u * a1) * 32u;
+					apply_row(*reinterpret_cast<const uint4*>(r), *reinterpret_cast<const uint32_t*>(r + 16), s);
+				}
+				s.C0 = fold_twists(s.C0); s.C1 = fold_twists(s.C1);
+			}
+			__syncwarp(__activemask());                                   // every lane's action row is consumed: the buffer head is free
+			store_state_simd(buf + lane * 20, s);                         // results packed [cube][20] at the head of the warp's buffer
+		}
+		__syncwarp();
+		{
+			// 32 cubes = 640 contiguous bytes in shared memory; out_pitch = 20: also contiguous in HBM (288: parked at the head of
+			// a 6x8x6 row for the rb686 render)
+			uint8_t* dst = reinterpret_cast<uint8_t*>(out) + chunk * 32 * out_pitch;
+			if (out_pitch == 20 && (reinterpret_cast<uintptr_t>(out) & 3u) == 0) {
+#pragma unroll
+				for (int t = 0; t < 5; ++t) {
+					const int j = lane + 32 * t;
+					if (j < cnt * 5) reinterpret_cast<uint32_t*>(dst)[j] = reinterpret_cast<const uint32_t*>(buf)[j];
+				}
+			} else if ((reinterpret_cast<uintptr_t>(out) & 3u) == 0 && (out_pitch & 3) == 0) {
+				for (int i = lane; i < cnt * 5; i += 32) {
+					const int c = i / 5, k = i - 5 * c;
+					*reinterpret_cast<uint32_t*>(dst + c * out_pitch + 4 * k) = reinterpret_cast<const uint32_t*>(buf)[i];
+				}
+			} else {
+				for (int i = lane; i < cnt * 20; i += 32) {
+					const int c = i / 20, k = i - 20 * c;
+					dst[c * out_pitch + k] = buf[i];
+				}
+			}
+		}
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		__syncwarp();
+		if (lane == 0 && chunk + stride < n_chunks) issue(chunk + stride);
+	}
+}
+
 static int env_int(const char* name, int dflt) {
 	const char* e = getenv(name);
 	return e ? atoi(e) : dflt;
@@ -362,6 +565,11 @@ static int ensure_device() {
 	const Host& h = host();
 	if (!h.ok) return rb_fail(RB_ERR_BAD_ARG, "macro-move table: corner twist is not additive for these move tables%s%s");
 	RB_CUDA(cudaMemcpyToSymbol(g_macro, h.rows, sizeof(h.rows)));
+	RB_CUDA(cudaMemcpyToSymbol(g_macro3, h.rows3, sizeof(h.rows3)));
+	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro3<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro3<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro3<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro3<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
 	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
 	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
 	done[dev] = true;
@@ -380,9 +588,36 @@ static int warps_for(int64_t n, int depth) {
 	return (int)w;
 }
 
+// 3-move kernel: fixed shared memory and warps per CTA for a given depth (0: use the 2-move kernel)
+static int64_t fixed_smem3(int r2) { return (int64_t)kP1Bytes3 + (int64_t)kP2Rows3 * 4 * r2 + kTailBytes + kMaxThreads / 32 * 8; }
+static int warps_for3(int64_t n, int depth, int r2) {
+	if (depth < 20) return 0;
+	int64_t w = (kSmemBudget - fixed_smem3(r2)) / (32 * (int64_t)depth);
+	if (w > max_threads() / 32) w = max_threads() / 32;
+	if (w < 8) return 0;                         // long sequences: too few resident warps to hide the table latency
+	const int64_t spread = ((n + 31) / 32 + RB_NUM_SMS - 1) / RB_NUM_SMS;
+	if (w > spread) w = spread;
+	return (int)w;
+}
+
 static int launch(const uint8_t* actions, int8_t* out, int64_t n, int depth, cudaStream_t st, int out_pitch = 20) {
 	int rc = ensure_device();
 	if (rc != RB_OK) return rc;
+	static const int rows_per = env_int("RB_SCRAMBLE_MOVES_PER_ROW", 3), r2_env = env_int("RB_SCRAMBLE_R2", 1);
+	const int r2 = (depth % 4 == 0 && (r2_env == 2 || r2_env == 4)) ? r2_env : 1;
+	const int W3 = rows_per == 3 ? warps_for3(n, depth, r2) : 0;
+	if (W3 > 0) {
+		const int64_t ctas = ((n + 31) / 32 + W3 - 1) / W3;
+		const int grid = (int)(ctas < RB_NUM_SMS ? ctas : RB_NUM_SMS);
+		size_t smem = (size_t)fixed_smem3(r2) + (size_t)W3 * 32 * depth;
+		if (smem < (size_t)kMinSmem3) smem = kMinSmem3;
+		if (depth % 4 != 0) k_scramble_macro3<false, 1><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch);
+		else if (r2 == 1) k_scramble_macro3<true, 1><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch);
+		else if (r2 == 2) k_scramble_macro3<true, 2><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch);
+		else k_scramble_macro3<true, 4><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch);
+		RB_LAUNCHED("scramble_macro3_2024");
+		return RB_OK;
+	}
 	const int W = warps_for(n, depth);
 	const int64_t ctas = ((n + 31) / 32 + W - 1) / W;
 	const int grid = (int)(ctas < RB_NUM_SMS ? ctas : RB_NUM_SMS);

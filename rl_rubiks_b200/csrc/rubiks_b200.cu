@@ -47,6 +47,13 @@ int rb_get_macro_table(uint32_t* rows) {
 	memcpy(rows, h.rows, sizeof(uint32_t) * rbs::kRows * rbs::kRowWords);
 	return RB_OK;
 }
+int rb_get_macro3_table(uint32_t* rows) {
+	RB_REQUIRE(rows, "null output");
+	const rbs::Host& h = rbs::host();
+	if (!h.ok) return rb_fail(RB_ERR_BAD_ARG, "macro-move table: corner twist is not additive for these move tables%s%s");
+	memcpy(rows, h.rows3, sizeof(uint32_t) * rbs::kRows3 * rbs::kRowWords);
+	return RB_OK;
+}
 int rb_get_stickers686(uint8_t* corner_home, uint8_t* corner_dst, uint8_t* edge_home, uint8_t* edge_dst) {
 	RB_REQUIRE(corner_home && corner_dst && edge_home && edge_dst, "null output");
 	const rbt::Tables& t = rbt::host();

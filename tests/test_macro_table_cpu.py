@@ -15,6 +15,13 @@ def _table():
 	return rows
 
 
+def _table3():
+	from rl_rubiks_b200 import _native as N
+	rows = np.empty((12 ** 3, 5), dtype=np.uint32)
+	N.check(N.lib.rb_get_macro3_table(rows.ctypes.data))
+	return rows
+
+
 def _prmt(a, b, sel):
 	"""Byte gather from the 8 bytes {a (0-3), b (4-7)} with 4 selector nibbles; a, b: (n, 4) uint8, sel: (n,) uint32."""
 	src = np.concatenate([a, b], axis=1)
@@ -35,15 +42,32 @@ def _fold(c):
 	return ((c & 0xe0) | t.astype(np.uint8)).astype(np.uint8)
 
 
-def _emulate(actions, rows):
+def _row_stream(actions, rows, rows3):
+	"""The table rows a cube's action sequence selects, in order: 2-move rows (identity padded), or 3-move rows with the
+	trailing depth % 3 moves taken from the 2-move table (k_scramble_macro3)."""
 	n, depth = actions.shape
-	pad = (-depth) % 2
-	a = np.concatenate([actions, np.full((n, pad), 12, np.uint8)], axis=1).astype(np.int64)
+	a = actions.astype(np.int64)
+	if rows3 is None:
+		pad = (-depth) % 2
+		a = np.concatenate([a, np.full((n, pad), 12, np.int64)], axis=1)
+		for m in range(0, depth + pad, 2):
+			yield rows[a[:, m] + 13 * a[:, m + 1]]
+		return
+	m = 0
+	for m in range(0, depth - depth % 3, 3):
+		yield rows3[a[:, m] + 12 * a[:, m + 1] + 144 * a[:, m + 2]]
+	m = depth - depth % 3
+	if m < depth:
+		a1 = a[:, m + 1] if m + 1 < depth else np.full(n, 12, np.int64)
+		yield rows[a[:, m] + 13 * a1]
+
+
+def _emulate(actions, rows, rows3=None, fold_every=10):
+	n, depth = actions.shape
 	C = np.tile((np.arange(8, dtype=np.uint8) << 5).astype(np.uint8), (n, 1))      # twist accumulator | id << 5
 	E = np.tile(np.arange(12, dtype=np.uint8), (n, 1))                             # id | flip << 4
 	steps = 0
-	for m in range(0, depth + pad, 2):
-		r = rows[a[:, m] + 13 * a[:, m + 1]]
+	for r in _row_stream(actions, rows, rows3):
 		sc, tf = r[:, 0], r[:, 4]
 		c0 = _prmt(C[:, :4], C[:, 4:], sc).astype(np.int64) + _bytes_of(tf & 0x03030303)
 		c1 = _prmt(C[:, :4], C[:, 4:], sc >> 16).astype(np.int64) + _bytes_of((tf >> 2) & 0x03030303)
@@ -57,7 +81,7 @@ def _emulate(actions, rows):
 			Es.append(e ^ _bytes_of(tf & (0x10101010 << d)))                    # partial flip bit 4 + d
 		E = np.concatenate(Es, 1)
 		steps += 1
-		if steps == 10:                                                            # kReduceEvery
+		if steps == fold_every:                                                    # kReduceEvery (2-move rows) / 8 (3-move rows)
 			steps, C = 0, _fold(C)
 	out = np.zeros((n, 20), dtype=np.int8)
 	rows_i = np.arange(n)
@@ -77,6 +101,16 @@ def test_macro_scramble_emulation_matches_oracle(depth):
 	actions = g.randint(0, 12, (300, depth)).astype(np.uint8)
 	f, d = O.indices_to_actions(actions)
 	assert (_emulate(actions, rows) == O.scramble_many(f, d, True)).all()
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3, 4, 5, 11, 12, 13, 24, 25, 26, 100, 250])
+def test_macro3_scramble_emulation_matches_oracle(depth):
+	"""3-move rows (12^3) with the depth % 3 tail from the 2-move table; the kernel folds after every 8 rows (24 moves)."""
+	rows, rows3 = _table(), _table3()
+	g = np.random.RandomState(1000 + depth)
+	actions = g.randint(0, 12, (300, depth)).astype(np.uint8)
+	f, d = O.indices_to_actions(actions)
+	assert (_emulate(actions, rows, rows3, fold_every=8) == O.scramble_many(f, d, True)).all()
 
 
 def test_macro_table_rows_are_permutations():
