@@ -84,6 +84,23 @@ def reduce_stats(stats: dict, op: str = "sum", device=None) -> dict:
 	return {k: float(v) for k, v in zip(keys, t.tolist())}
 
 
+def allreduce_mean_(tensors) -> None:
+	"""In-place mean over ranks of a list of same-dtype tensors (the gradients of one minibatch in data-parallel training,
+	rl_rubiks_b200.train) with ONE collective: flatten, all-reduce(SUM), scale, scatter back.  No-op without a process group."""
+	rank, ws = world()
+	tensors = [t for t in tensors if t is not None]
+	if ws == 1 or not tensors:
+		return
+	flat = torch.cat([t.reshape(-1) for t in tensors])
+	dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+	flat.div_(ws)
+	o = 0
+	for t in tensors:
+		n = t.numel()
+		t.copy_(flat[o:o + n].view_as(t))
+		o += n
+
+
 def sharded_apply(fn, *arrays, axis: int = 0, gather: bool = True, device=None):
 	"""Runs `fn` on this rank's slice of every array (sliced along `axis`) and, if `gather`, returns the rank-ordered
 	concatenation of the per-rank results on every rank.  `fn` returns one array/tensor whose rows are units.

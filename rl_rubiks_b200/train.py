@@ -1,0 +1,157 @@
+"""
+Device-resident Autodidactic-Iteration training loop: mirror of `Train.train` (reference: librubiks/train.py:111-247)
+around the fused ADI generator.
+
+What changes against the reference: the ADI batch is born on the GPU (`adi.ADIGenerator`, buffers allocated once), so the
+four `.to(gpu)` copies of train.py:156-159 and the `.cpu()` of train.py:304 are gone, and the per-minibatch
+`.detach().cpu().numpy().mean()` (train.py:178-179, one host sync per minibatch) becomes one device accumulation read back
+once per rollout.  What stays exactly the reference's: the rollout loop, the tau-mixed generator net (train.py:341-352),
+minibatch slicing (`_get_batches`, train.py:400-410 -- including its unused `np.random.shuffle`, which advances the global
+numpy stream the next rollout's scramble draws from), loss = mean((CE + MSE) * loss_weights), the lr / alpha schedule
+(train.py:191-202), evaluation rollouts (train.py:63-73) and best-net bookkeeping (train.py:211-227).  The network forward /
+backward stays torch (dense GEMMs).
+
+Data-parallel use (one process per GPU): every rank generates its own share of the games and gradients are averaged with
+one flat NCCL all-reduce per minibatch (`sharding.allreduce_mean_`); there is no collective on the ADI path.
+"""
+from __future__ import annotations
+
+import copy
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import adi, sharding
+
+
+def _clone(net):
+	"""Model.clone() (model.py:163-169) when the net has it, else a deep copy."""
+	return net.clone() if hasattr(net, "clone") else copy.deepcopy(net)
+
+
+class Train:
+	"""Same constructor arguments as the reference's `Train` (train.py:28-46) minus logging / analysis; `agent` and
+	`evaluator` are optional and duck-typed (`evaluator.eval(agent) -> (results, states, times)`, `agent.net`)."""
+
+	def __init__(self, rollouts: int, batch_size: int, rollout_games: int, rollout_depth: int, optim_fn, alpha_update: float,
+				 lr: float, gamma: float, update_interval: int, tau: float, reward_method: str, agent=None, evaluator=None,
+				 evaluation_interval: int = 0, policy_criterion=torch.nn.CrossEntropyLoss, value_criterion=torch.nn.MSELoss,
+				 data_parallel: bool = False, log=None):
+		N.require_cuda()
+		self.rollouts = int(rollouts)
+		self.train_rollouts = np.arange(self.rollouts)
+		self.rollout_games, self.rollout_depth = int(rollout_games), int(rollout_depth)
+		self.states_per_rollout = self.rollout_depth * self.rollout_games
+		self.batch_size = self.states_per_rollout if not batch_size else int(batch_size)      # train.py:58
+		self.adi_ff_batches = 1
+		self.reward_method = reward_method
+		self.evaluation_rollouts = self.evaluation_schedule(self.rollouts, evaluation_interval)
+		self.agent, self.evaluator = agent, evaluator
+		self.tau, self.alpha_update, self.lr, self.gamma, self.update_interval = tau, alpha_update, lr, gamma, update_interval
+		self.optim = optim_fn
+		self.policy_criterion = policy_criterion(reduction="none")
+		self.value_criterion = value_criterion(reduction="none")
+		self.data_parallel = bool(data_parallel)
+		self.log = log or (lambda *a, **k: None)
+		self.alphas, self.lrs = [], []
+
+	@staticmethod
+	def evaluation_schedule(rollouts: int, evaluation_interval: int) -> np.ndarray:
+		"""train.py:63-73: evaluate every `evaluation_interval` rollouts and after the last one."""
+		if not evaluation_interval:
+			return np.array([])
+		ev = np.arange(0, rollouts, evaluation_interval) - 1
+		if evaluation_interval == 1:
+			ev = ev[1:]
+		else:
+			ev[0] = 0
+		if not len(ev) or rollouts - 1 != ev[-1]:
+			ev = np.append(ev, rollouts - 1)
+		return ev
+
+	@staticmethod
+	def _get_batches(size: int, bsize: int):
+		"""train.py:400-410.  The shuffle is never used for indexing there either; it is kept because it consumes the
+		global numpy stream between two rollouts' scramble draws."""
+		nbatches = int(np.ceil(size / bsize))
+		idcs = np.arange(size)
+		np.random.shuffle(idcs)
+		batches = [slice(b * bsize, (b + 1) * bsize) for b in range(nbatches)]
+		batches[-1] = slice(batches[-1].start, size)
+		return batches
+
+	@torch.no_grad()
+	def _update_gen_net(self, generator_net, net):
+		"""train.py:341-352: generator <- tau * net + (1 - tau) * generator, over the whole state dict (buffers included)."""
+		gen, cur = generator_net.state_dict(), net.state_dict()
+		for name, p in cur.items():
+			gen[name].data.copy_(self.tau * p.data + (1 - self.tau) * gen[name].data)
+		generator_net.load_state_dict(gen)
+		return generator_net
+
+	def ADI_traindata(self, net, alpha: float):
+		"""train.py:256-339 on the device (rl_rubiks_b200.adi): (oh_states, policy_targets, value_targets, loss_weights)."""
+		return adi.adi_traindata(net, self.rollout_games, self.rollout_depth, self.reward_method, alpha,
+								 ff_batches=self.adi_ff_batches, generator=self._generator)
+
+	def train(self, net):
+		"""Returns (net after the last rollout, net with the best evaluation score), as train.py:111-247."""
+		dev = torch.device("cuda", torch.cuda.current_device())
+		self._generator = adi.ADIGenerator(self.rollout_games, self.rollout_depth, self.reward_method)
+		best_solve, best_net = 0, _clone(net)
+		if self.agent is not None:
+			self.agent.net = net
+		generator_net = _clone(net)
+		alpha = 1 if self.alpha_update == 1 else 0
+		optimizer = self.optim(net.parameters(), lr=self.lr)
+		lr_scheduler = torch.optim.lr_scheduler.StepLR(optimizer, 1, self.gamma)
+		self.policy_losses, self.value_losses = np.zeros(self.rollouts), np.zeros(self.rollouts)
+		self.train_losses = np.empty(self.rollouts)
+		self.sol_percents, self.alphas, self.lrs = [], [], []
+		params = [p for p in net.parameters() if p.requires_grad]
+		acc = torch.zeros(2, dtype=torch.float64, device=dev)
+
+		for rollout in range(self.rollouts):
+			generator_net = self._update_gen_net(generator_net, net) if self.tau != 1 else net
+			self.alphas.append(float(alpha))
+			self.lrs.append(float(optimizer.param_groups[0]["lr"]))
+			training_data, policy_targets, value_targets, loss_weights = self.ADI_traindata(generator_net, alpha)
+
+			net.train()
+			batches = self._get_batches(self.states_per_rollout, self.batch_size)
+			acc.zero_()
+			for batch in batches:
+				optimizer.zero_grad()
+				policy_pred, value_pred = net(training_data[batch], policy=True, value=True)
+				policy_loss = self.policy_criterion(policy_pred, policy_targets[batch]) * loss_weights[batch]
+				value_loss = self.value_criterion(value_pred.squeeze(), value_targets[batch]) * loss_weights[batch]
+				loss = torch.mean(policy_loss + value_loss)
+				loss.backward()
+				if self.data_parallel:
+					sharding.allreduce_mean_([p.grad for p in params if p.grad is not None])
+				optimizer.step()
+				# train.py:178-179 without the per-minibatch device->host sync: f32 means accumulated in f64 on the device
+				acc[0] += policy_loss.detach().mean().double() / len(batches)
+				acc[1] += value_loss.detach().mean().double() / len(batches)
+			self.policy_losses[rollout], self.value_losses[rollout] = acc.tolist()
+			self.train_losses[rollout] = self.policy_losses[rollout] + self.value_losses[rollout]
+
+			if rollout and self.update_interval and rollout % self.update_interval == 0:       # train.py:191-202
+				if self.gamma != 1:
+					lr_scheduler.step()
+				if (alpha + self.alpha_update <= 1 or np.isclose(alpha + self.alpha_update, 1)) and self.alpha_update:
+					alpha += self.alpha_update
+				elif alpha < 1 and alpha + self.alpha_update > 1 and self.alpha_update:
+					alpha = 1
+			self.log(f"Rollout {rollout} completed with mean loss {self.train_losses[rollout]}")
+
+			if rollout in self.evaluation_rollouts and self.evaluator is not None and self.agent is not None:   # train.py:211-227
+				net.eval()
+				self.agent.net = net
+				eval_results, _, _ = self.evaluator.eval(self.agent)
+				eval_reward = (np.asarray(eval_results) != -1).mean()
+				self.sol_percents.append(eval_reward)
+				if eval_reward > best_solve:
+					best_solve, best_net = eval_reward, _clone(net)
+		return net, best_net

@@ -293,10 +293,60 @@ def gen_search():
 	save("search", **out)
 
 
+def gen_train():
+	"""Train.train (train.py:111-247) run end to end on the CPU with a narrowed fc net (same layer pattern as fc_small,
+	model.py:117-161, sizes 480 -> 64 -> 32 -> {16 -> 12, 16 -> 1} so that the initial weights fit a fixture): the per-rollout
+	losses, the lr / alpha schedule it implies and the final parameters.  tau < 1 exercises the generator-net mix, the 30
+	states of a rollout split into minibatches of 16 + 14."""
+	from librubiks.model import Model, ModelConfig
+	from librubiks.train import Train
+	cube.set_is2024(True)
+	ModelConfig._fc_small_arch = {"shared_sizes": [64, 32], "part_sizes": [16]}
+	out = {}
+	for tag, kw in (("a", dict(rollouts=4, batch_size=16, rollout_games=6, rollout_depth=5, alpha_update=0.25, lr=5e-3, gamma=0.5,
+							   update_interval=1, tau=0.5, reward_method="lapanfix")),
+					("b", dict(rollouts=3, batch_size=20, rollout_games=5, rollout_depth=4, alpha_update=1, lr=1e-2, gamma=1,
+							   update_interval=2, tau=1, reward_method="paper"))):
+		torch.manual_seed(7)
+		net = Model.create(ModelConfig())
+		init = {k: v.clone().numpy() for k, v in net.state_dict().items()}
+
+		class _Agent:
+			net = None
+		t = Train(optim_fn=torch.optim.Adam, agent=_Agent(), evaluator=None, evaluation_interval=0, with_analysis=False, **kw)
+		# (batch_size=0, "one batch per rollout", crashes in the reference: train.py:58 reads states_per_rollout before
+		# train.py:125 sets it -- case b passes the full rollout size instead)
+		np.random.seed(42)
+		trained, _ = t.train(net)
+		for k, v in init.items():
+			out[f"{tag}_init_{k}"] = v
+		for k, v in trained.state_dict().items():
+			out[f"{tag}_final_{k}"] = v.numpy()
+		out[f"{tag}_policy_losses"], out[f"{tag}_value_losses"], out[f"{tag}_train_losses"] = t.policy_losses, t.value_losses, t.train_losses
+		out[f"{tag}_kw"] = np.array(json.dumps(kw))
+	save("train", **out)
+
+
+def gen_eval():
+	"""Evaluator.eval (evaluation.py:54-94) with the A* agent and the integer fake value net: results (turns or -1) and
+	states explored per game, for fixed depths and for the deep (depth ~ U[100, 999]) mode."""
+	from librubiks.solving.evaluation import Evaluator
+	cube.set_is2024(True)
+	out = {}
+	for tag, depths, n_games, max_states in (("fixed", [1, 3, 5], 3, 3000), ("deep", range(0), 2, 500)):
+		net = FakeNet(480, seed=11)
+		agent = agents.AStar(net, lambda_=0.2, expansions=20)
+		ev = Evaluator(n_games=n_games, scrambling_depths=depths, max_time=None, max_states=max_states)
+		np.random.seed(9)
+		res, states, _ = ev.eval(agent)
+		out[f"{tag}_res"], out[f"{tag}_states"], out[f"{tag}_w"] = res, states, net.w.numpy()
+		out[f"{tag}_max_states"], out[f"{tag}_n_games"] = np.int64(max_states), np.int64(n_games)
+		out[f"{tag}_depths"] = np.array(list(depths), dtype=np.int64)
+	save("evaluation", **out)
+
+
 if __name__ == "__main__":
 	torch.manual_seed(0)
-	gen_tables()
-	gen_dynamics()
-	gen_scramblers()
-	gen_adi()
-	gen_search()
+	which = sys.argv[1:] or ["tables", "dynamics", "scramblers", "adi", "search", "train", "eval"]
+	for name in which:
+		globals()["gen_" + name]()

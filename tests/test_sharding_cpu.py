@@ -85,3 +85,35 @@ def test_two_rank_gloo_shard_gather_reduce(n):
 		assert out["stats"] == {"cubes": float(n), "moves": float(n * depth)}
 		assert out["tmax"] == {"ms": 11.0}
 		assert out["mine_shape"] == (depth, out["hi"] - out["lo"]) and out["mine_ok"]
+
+
+def _grad_worker(rank, ws, port, ret):
+	os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws))
+	dist.init_process_group("gloo", rank=rank, world_size=ws)
+	try:
+		torch.manual_seed(0)                                            # same replica and same full batch on every rank
+		net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ELU(), torch.nn.Linear(5, 1))
+		x, y = torch.randn(8, 6), torch.randn(8, 1)
+		lo, hi = S.shard_bounds(8, ws, rank)
+		torch.nn.functional.mse_loss(net(x[lo:hi]), y[lo:hi]).backward()            # mean over this rank's half
+		grads = [p.grad for p in net.parameters()]
+		S.allreduce_mean_(grads)
+		ret[rank] = [g.clone().numpy() for g in grads]
+	finally:
+		dist.destroy_process_group()
+
+
+def test_two_rank_gradient_mean_equals_full_batch_gradient():
+	"""Data-parallel training (rl_rubiks_b200.train): the rank-mean of per-shard mean-loss gradients is the full-batch gradient."""
+	mgr = mp.Manager()
+	ret = mgr.dict()
+	mp.spawn(_grad_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+	torch.manual_seed(0)
+	net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ELU(), torch.nn.Linear(5, 1))
+	x, y = torch.randn(8, 6), torch.randn(8, 1)
+	torch.nn.functional.mse_loss(net(x), y).backward()
+	want = [p.grad.numpy() for p in net.parameters()]
+	for r in range(2):
+		for a, b in zip(ret[r], want):
+			np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-7)
+	S.allreduce_mean_([torch.ones(3)])                                  # no process group: no-op
