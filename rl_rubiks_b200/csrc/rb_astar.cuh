@@ -65,14 +65,55 @@ __device__ __forceinline__ bool lex_less(unsigned long long ka, uint32_t ia, uns
 }
 
 // ---- pop: the N smallest (cost, index) of the open list, ascending ------------------------------------------------------
-// One block per search.  Shared memory holds 2048 (key, index) pairs: the running best 1024 (ascending) and the current
-// chunk of 1024 candidates.  A chunk is sorted descending, [best | chunk] is then bitonic and one merge keeps the best 1024.
-// Chunks whose candidates all lie above the current N-th key are skipped after a ballot.
+// One block per search.  The open list is scanned once, 2048 entries per round (two coalesced loads in flight per thread);
+// an entry that beats the running threshold -- the N-th best (key, index) so far, INF until N candidates were merged -- is
+// appended to a staging buffer in shared memory.  Only when 1024 candidates are staged (or the scan ends) are they sorted
+// (bitonic, descending) and merged into the running best 1024 (ascending): [best | chunk] is then bitonic and one merge
+// network keeps the lower half.  With a tightening threshold the number of sort + merge rounds is ~(N / 1024)(1 + ln(n / N))
+// instead of one per 1024 open entries.  Ties are broken by index, so the result does not depend on the staging order.
+constexpr int kStage = 3072;                     // < 1024 left over + at most 2048 staged per round
+constexpr int kSelSmem = (2048 + kStage) * (8 + 4) + 16;
+
+__device__ __forceinline__ void sort_merge_1024(unsigned long long* s_key, uint32_t* s_idx, int t) {
+	// bitonic sort of [1024, 2048), descending
+	for (int size = 2; size <= 1024; size <<= 1)
+		for (int stride = size >> 1; stride > 0; stride >>= 1) {
+			const int j = t ^ stride;
+			if (j > t) {
+				const bool up = (t & size) != 0;                // mirrored direction bits => descending overall
+				const int a = 1024 + t, b = 1024 + j;
+				const bool a_gt_b = lex_less(s_key[b], s_idx[b], s_key[a], s_idx[a]);
+				if (a_gt_b == up) {
+					const unsigned long long tk = s_key[a]; s_key[a] = s_key[b]; s_key[b] = tk;
+					const uint32_t ti = s_idx[a]; s_idx[a] = s_idx[b]; s_idx[b] = ti;
+				}
+			}
+			__syncthreads();
+		}
+	// [best ascending | chunk descending] is bitonic: merge to ascending over all 2048, keep the lower half
+	for (int stride = 1024; stride > 0; stride >>= 1) {
+#pragma unroll
+		for (int r = 0; r < 2; ++r) {
+			const int e = t + 1024 * r, j = e ^ stride;
+			if (j > e) {
+				if (lex_less(s_key[j], s_idx[j], s_key[e], s_idx[e])) {
+					const unsigned long long tk = s_key[e]; s_key[e] = s_key[j]; s_key[j] = tk;
+					const uint32_t ti = s_idx[e]; s_idx[e] = s_idx[j]; s_idx[j] = ti;
+				}
+			}
+		}
+		__syncthreads();
+	}
+}
+
 __global__ void __launch_bounds__(kSelThreads)
 k_select(View v, int64_t max_states, int32_t* __restrict__ n_active) {
-	__shared__ unsigned long long s_key[2048];
-	__shared__ uint32_t s_idx[2048];
-	__shared__ int s_any;
+	extern __shared__ __align__(16) uint8_t sel_smem[];
+	unsigned long long* s_key = reinterpret_cast<unsigned long long*>(sel_smem);               // [2048]: best | sort area
+	unsigned long long* st_key = s_key + 2048;                                                  // [kStage]
+	uint32_t* s_idx = reinterpret_cast<uint32_t*>(st_key + kStage);                             // [2048]
+	uint32_t* st_idx = s_idx + 2048;                                                            // [kStage]
+	int* s_cnt = reinterpret_cast<int*>(st_idx + kStage);
 	const int s = blockIdx.x, t = threadIdx.x;
 	const int cnt = v.count[s];
 	const bool active = !v.won[s] && cnt > 0 && (int64_t)cnt + v.P() <= max_states;
@@ -83,59 +124,47 @@ k_select(View v, int64_t max_states, int32_t* __restrict__ n_active) {
 	const double* cost = v.cost + (int64_t)s * v.M;
 	uint8_t* in_open = v.in_open + (int64_t)s * v.M;
 	s_key[t] = kInfKey; s_idx[t] = 0xffffffffu;
+	if (t == 0) *s_cnt = 0;
 	__syncthreads();
-	for (int base = 1; base <= cnt; base += kSelThreads) {
-		const int idx = base + t;
-		unsigned long long k = kInfKey;
-		if (idx <= cnt && in_open[idx]) k = sortable(cost[idx]);
-		// running threshold: the N-th best so far (INF until N candidates were seen)
+	// moves the last min(staged, 1024) candidates into the sort area (INF padded) and merges them into the best
+	auto flush = [&](int staged) {
+		const int take = staged < 1024 ? staged : 1024, from = staged - take;
+		if (t < take) { s_key[1024 + t] = st_key[from + t]; s_idx[1024 + t] = st_idx[from + t]; }
+		else { s_key[1024 + t] = kInfKey; s_idx[1024 + t] = 0xffffffffu; }
+		__syncthreads();
+		if (t == 0) *s_cnt = from;
+		sort_merge_1024(s_key, s_idx, t);                          // ends with a barrier
+	};
+	for (int base = 1; base <= cnt; base += 2 * kSelThreads) {
 		const unsigned long long thr_k = s_key[v.N - 1];
 		const uint32_t thr_i = s_idx[v.N - 1];
-		if (k != kInfKey && !lex_less(k, (uint32_t)idx, thr_k, thr_i)) k = kInfKey;
-		if (t == 0) s_any = 0;
-		__syncthreads();
-		if (k != kInfKey) s_any = 1;
-		__syncthreads();
-		if (!s_any) continue;                                   // uniform: nothing in this chunk can be popped
-		s_key[1024 + t] = k; s_idx[1024 + t] = k != kInfKey ? (uint32_t)idx : 0xffffffffu;
-		__syncthreads();
-		// bitonic sort of the chunk, descending
-		for (int size = 2; size <= 1024; size <<= 1)
-			for (int stride = size >> 1; stride > 0; stride >>= 1) {
-				const int j = t ^ stride;
-				if (j > t) {
-					const bool up = (t & size) != 0;            // mirrored direction bits => descending overall
-					const int a = 1024 + t, b = 1024 + j;
-					const bool a_gt_b = lex_less(s_key[b], s_idx[b], s_key[a], s_idx[a]);
-					if (a_gt_b == up) {
-						const unsigned long long tk = s_key[a]; s_key[a] = s_key[b]; s_key[b] = tk;
-						const uint32_t ti = s_idx[a]; s_idx[a] = s_idx[b]; s_idx[b] = ti;
-					}
-				}
-				__syncthreads();
-			}
-		// [best ascending | chunk descending] is bitonic: merge to ascending over all 2048, keep the lower half
-		for (int stride = 1024; stride > 0; stride >>= 1) {
-#pragma unroll
-			for (int r = 0; r < 2; ++r) {
-				const int e = t + 1024 * r, j = e ^ stride;
-				if (j > e) {
-					if (lex_less(s_key[j], s_idx[j], s_key[e], s_idx[e])) {
-						const unsigned long long tk = s_key[e]; s_key[e] = s_key[j]; s_key[j] = tk;
-						const uint32_t ti = s_idx[e]; s_idx[e] = s_idx[j]; s_idx[j] = ti;
-					}
-				}
-			}
-			__syncthreads();
+		const int i0 = base + t, i1 = base + kSelThreads + t;
+		const bool o0 = i0 <= cnt && in_open[i0], o1 = i1 <= cnt && in_open[i1];
+		const double c0 = o0 ? cost[i0] : 0.0, c1 = o1 ? cost[i1] : 0.0;
+		if (o0) {
+			const unsigned long long k = sortable(c0);
+			if (lex_less(k, (uint32_t)i0, thr_k, thr_i)) { const int p = atomicAdd(s_cnt, 1); st_key[p] = k; st_idx[p] = (uint32_t)i0; }
 		}
+		if (o1) {
+			const unsigned long long k = sortable(c1);
+			if (lex_less(k, (uint32_t)i1, thr_k, thr_i)) { const int p = atomicAdd(s_cnt, 1); st_key[p] = k; st_idx[p] = (uint32_t)i1; }
+		}
+		__syncthreads();
+		int staged = *s_cnt;
+		__syncthreads();                                           // everyone has read the count before thread 0 rewrites it
+		while (staged >= 1024) { flush(staged); staged -= 1024; }
+	}
+	{
+		const int staged = *s_cnt;
+		__syncthreads();
+		if (staged > 0) flush(staged);
 	}
 	// pop
-	int n = 0;
 	if (t < v.N && s_key[t] != kInfKey) {
 		v.sel[(int64_t)s * v.N + t] = (int32_t)s_idx[t];
 		in_open[s_idx[t]] = 0;
 	}
-	n = __syncthreads_count(t < v.N && s_key[t] != kInfKey);
+	const int n = __syncthreads_count(t < v.N && s_key[t] != kInfKey);
 	if (t == 0) {
 		v.n_sel[s] = n;
 		if (n) atomicAdd(n_active, 1);

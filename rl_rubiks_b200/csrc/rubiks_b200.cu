@@ -523,7 +523,8 @@ int rb_astar_expand(const rb_astar_view* a, int64_t max_states, int8_t* new_stat
 	cudaStream_t st = S(stream);
 	const dim3 grid(v.nbx(), v.K);
 	RB_CUDA(cudaMemsetAsync(n_active, 0, sizeof(int32_t), st));
-	rba::k_select<<<v.K, rba::kSelThreads, 0, st>>>(v, max_states, n_active);
+	RB_CUDA(cudaFuncSetAttribute(rba::k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, rba::kSelSmem));   // per device, cheap
+	rba::k_select<<<v.K, rba::kSelThreads, rba::kSelSmem, st>>>(v, max_states, n_active);
 	RB_LAUNCHED("astar_select");
 	rba::k_probe<<<grid, rba::kThreads, 0, st>>>(v);
 	RB_LAUNCHED("astar_probe");
