@@ -118,6 +118,21 @@ int rb_sequence_scramble(int rep, const uint8_t* faces, const uint8_t* dirs, int
 int rb_adi_generate(int rep, const uint8_t* faces, const uint8_t* dirs, int32_t games, int32_t depth,
                     int32_t with_solved, int8_t* states, float* oh_states, int8_t* children,
                     float* children_oh, uint8_t* solved_states, uint8_t* solved_children, rb_stream_t stream);
+
+/* ---- bfloat16 one-hot variants ----------------------------------------------------------------
+ * Same functions with the one-hot emitted as bfloat16 (raw bits in uint16_t; 0.0 and 1.0 -- and every int8 value of a
+ * 6x8x6 state -- are exact in bf16, so the rows equal the f32 rows converted): half the HBM write traffic of the
+ * write-bound emitters and the input dtype of a bf16 tensor-core forward of the value/policy net (model.py:131-141).
+ * The reference emits f32 (cube.py:273-276, 368); these are an opt-in of the Python mirror (`as_oh(states, dtype=...)`,
+ * `ADIGenerator(oh_dtype=...)`). */
+int rb_as_oh_bf16(int rep, const int8_t* states, uint16_t* oh, int64_t n, rb_stream_t stream);
+int rb_expand12_bf16(int rep, const int8_t* states, int8_t* children, uint16_t* children_oh,
+                     uint8_t* solved, int64_t n, rb_stream_t stream);
+int rb_sequence_scramble_bf16(int rep, const uint8_t* faces, const uint8_t* dirs, int32_t games, int32_t depth,
+                              int32_t with_solved, int8_t* states, uint16_t* oh, uint8_t* solved, rb_stream_t stream);
+int rb_adi_generate_bf16(int rep, const uint8_t* faces, const uint8_t* dirs, int32_t games, int32_t depth,
+                         int32_t with_solved, int8_t* states, uint16_t* oh_states, int8_t* children,
+                         uint16_t* children_oh, uint8_t* solved_states, uint8_t* solved_children, rb_stream_t stream);
 /* Target assembly, train.py:292-296 + 313-325: values f32 [12n] are the net's outputs for the children;
  * rewards (+1 / 0 with reward0 for a solved child, -1 otherwise) are added in f32, the row argmax takes the
  * FIRST maximum (NaN counts as maximum, as torch.argmax), lapanfix zeroes targets of solved states,

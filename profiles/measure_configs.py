@@ -116,7 +116,9 @@ def main():
 		s = scrambled_2024(n)
 		oh = torch.empty(n, 480, dtype=torch.float32, device=dev)
 		report("as_oh_2024", n * 1940, n, "states", lambda: N.check(N.lib.rb_as_oh(N.REP_2024, N.ptr(s), N.ptr(oh), n, sh)), n=n)
-		del s, oh
+		ohb = torch.empty(n, 480, dtype=torch.bfloat16, device=dev)
+		report("as_oh_2024 bf16 rows (opt-in)", n * 980, n, "states", lambda: N.check(N.lib.rb_as_oh_bf16(N.REP_2024, N.ptr(s), N.ptr(ohb), n, sh)), n=n)
+		del s, oh, ohb
 	if want("expand12_2024"):
 		n = (1 << 18) // q
 		s = scrambled_2024(n)
@@ -159,7 +161,11 @@ def main():
 		tgt_bytes = 4 * 12 * nst + 12 * nst + nst + 12 * nst + 4 * nst
 		report(f"adi_generate_2024 ({games} x {depth})", gen_bytes, nst, "samples", gen.generate, n=nst)
 		report(f"adi_targets+loss_weights ({games} x {depth})", tgt_bytes, nst, "samples", lambda: gen.targets(values, 0.3), n=nst)
-		del gen, values
+		del gen
+		genb = adi.ADIGenerator(games, depth, "lapanfix", keep_states=True, oh_dtype=torch.bfloat16)
+		genb.set_actions(torch.randint(0, 12, (depth, games), dtype=torch.uint8, device=dev, generator=g))
+		report(f"adi_generate_2024 bf16 rows (opt-in) ({games} x {depth})", 960 * 13 * nst + 20 * nst + 13 * nst + nst, nst, "samples", genb.generate, n=nst)
+		del genb, values
 
 	# ---- C3 6x8x6 ----
 	if want("686"):

@@ -44,6 +44,10 @@ SIGNATURES = {
 	"rb_scramble": (C.c_int, [C.c_int, _p, _i64, _i64, _p, _p, _i64, _i32, _p]),
 	"rb_sequence_scramble": (C.c_int, [C.c_int, _p, _p, _i32, _i32, _i32, _p, _p, _p, _p]),
 	"rb_adi_generate": (C.c_int, [C.c_int, _p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p]),
+	"rb_as_oh_bf16": (C.c_int, [C.c_int, _p, _p, _i64, _p]),
+	"rb_expand12_bf16": (C.c_int, [C.c_int, _p, _p, _p, _p, _i64, _p]),
+	"rb_sequence_scramble_bf16": (C.c_int, [C.c_int, _p, _p, _i32, _i32, _i32, _p, _p, _p, _p]),
+	"rb_adi_generate_bf16": (C.c_int, [C.c_int, _p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p]),
 	"rb_adi_targets": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _p, _p, _p]),
 	"rb_adi_targets_weights": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _f64, _f64, _p, _p, _p, _p]),
 	"rb_adi_weight_sum": (_f64, [_i32, _i32]),

@@ -20,7 +20,7 @@ class ADIGenerator:
 	"""Pre-allocates every buffer of one ADI rollout (games x depth states) on the current device."""
 
 	def __init__(self, games: int, depth: int, reward_method: str = "lapanfix", keep_states: bool = False,
-				 keep_children: bool = False, is2024: bool | None = None):
+				 keep_children: bool = False, is2024: bool | None = None, oh_dtype=torch.float32):
 		N.require_cuda()
 		if reward_method not in N.REWARD_METHODS:
 			raise KeyError(f"reward_method must be one of {list(N.REWARD_METHODS)}, got {reward_method!r}")
@@ -32,8 +32,10 @@ class ADIGenerator:
 		n = self.n = self.games * self.depth
 		dev = torch.device("cuda", torch.cuda.current_device())
 		self.actions = torch.empty(self.depth, self.games, dtype=torch.uint8, device=dev)
-		self.oh_states = torch.empty(n, self.width, dtype=torch.float32, device=dev)
-		self.children_oh = torch.empty(12 * n, self.width, dtype=torch.float32, device=dev)
+		self.oh_dtype = oh_dtype                 # torch.float32 (the reference's) or torch.bfloat16 (opt-in, same 0/1 rows)
+		self._generate_fn = cube._oh_fn("rb_adi_generate", oh_dtype)
+		self.oh_states = torch.empty(n, self.width, dtype=oh_dtype, device=dev)
+		self.children_oh = torch.empty(12 * n, self.width, dtype=oh_dtype, device=dev)
 		self.solved_states = torch.empty(n, dtype=torch.uint8, device=dev)
 		self.solved_children = torch.empty(12 * n, dtype=torch.uint8, device=dev)
 		self.states = torch.empty(n, *shape, dtype=torch.int8, device=dev) if keep_states else None
@@ -66,7 +68,7 @@ class ADIGenerator:
 
 	def generate(self):
 		"""Kernel A (train.py:277-296).  Returns (oh_states, children_oh)."""
-		N.check(N.lib.rb_adi_generate(self.rep, N.ptr(self.actions), None, self.games, self.depth, int(self.with_solved),
+		N.check(self._generate_fn(self.rep, N.ptr(self.actions), None, self.games, self.depth, int(self.with_solved),
 									  N.ptr(self.states), N.ptr(self.oh_states), N.ptr(self.children), N.ptr(self.children_oh),
 									  N.ptr(self.solved_states), N.ptr(self.solved_children), N.stream_handle()))
 		return self.oh_states, self.children_oh

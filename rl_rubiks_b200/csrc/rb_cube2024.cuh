@@ -240,6 +240,28 @@ __device__ __forceinline__ void warp_write_oh_row(float* __restrict__ row, uint3
 	}
 }
 
+// bf16 rows (0x3F80 = 1.0, exact): 960 bytes = 60 x 16-byte chunks of 8 columns, lane l owns chunks l and l + 32.  Chunk c
+// covers columns 8c..8c+7 inside cubie j = c/3 at offset 8*(c%3).  Same bits as the f32 row rounded to bf16.
+typedef uint16_t rb_bf16;                       // raw bfloat16 bits at the C ABI
+__device__ __forceinline__ void warp_write_oh_row(rb_bf16* __restrict__ row, uint32_t v, int lane, int pol) {
+	uint4* dst = reinterpret_cast<uint4*>(row);
+#pragma unroll
+	for (int k = 0; k < 2; ++k) {
+		const int c = lane + 32 * k;
+		const int j = c / 3;
+		const uint32_t vj = __shfl_sync(0xffffffffu, v, j < 20 ? j : 0);
+		const uint32_t off = vj - 8u * (uint32_t)(c - 3 * j);
+		if (c < kOhWidth / 8) {
+			uint4 o;
+			o.x = off == 0u ? 0x00003F80u : (off == 1u ? 0x3F800000u : 0u);
+			o.y = off == 2u ? 0x00003F80u : (off == 3u ? 0x3F800000u : 0u);
+			o.z = off == 4u ? 0x00003F80u : (off == 5u ? 0x3F800000u : 0u);
+			o.w = off == 6u ? 0x00003F80u : (off == 7u ? 0x3F800000u : 0u);
+			rb_st_stream(dst + c, o, pol);
+		}
+	}
+}
+
 // Lane j < 20 holds cubie j of the state at `p` (int8[20]); other lanes hold 0xff.
 __device__ __forceinline__ uint32_t warp_load_state(const int8_t* __restrict__ p, int lane) {
 	return lane < 20 ? (uint32_t)(uint8_t)p[lane] : 0xffu;
@@ -260,8 +282,9 @@ __device__ __forceinline__ uint32_t warp_move(const uint8_t* s_lut, uint32_t a, 
 // thread, coalesced, fetched one tile ahead into registers so that the read latency -- several microseconds under a
 // saturating write stream -- is paid once per 480 KB of output and hidden behind it); warp w then emits rows w, w+8, ...
 // of the tile, so the block's eight warps sweep one contiguous region of the output.
+template <typename OH>
 __global__ void __launch_bounds__(kThreads)
-k_as_oh(const int8_t* __restrict__ in, float* __restrict__ oh, int64_t n, int pol) {
+k_as_oh(const int8_t* __restrict__ in, OH* __restrict__ oh, int64_t n, int pol) {
 	__shared__ __align__(16) uint32_t s_tile[2][kThreads * 5];
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	const int64_t n_tiles = (n + kThreads - 1) / kThreads;
@@ -291,8 +314,9 @@ k_as_oh(const int8_t* __restrict__ in, float* __restrict__ oh, int64_t n, int po
 }
 
 // Any-alignment version: one warp per state, byte loads.
+template <typename OH>
 __global__ void __launch_bounds__(kThreads)
-k_as_oh_any(const int8_t* __restrict__ in, float* __restrict__ oh, int64_t n, int pol) {
+k_as_oh_any(const int8_t* __restrict__ in, OH* __restrict__ oh, int64_t n, int pol) {
 	const int lane = threadIdx.x & 31;
 	const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
 	const int64_t n_warps = (int64_t)gridDim.x * (kThreads / 32);
@@ -306,8 +330,9 @@ k_as_oh_any(const int8_t* __restrict__ in, float* __restrict__ oh, int64_t n, in
 // expand12 (+ fused one-hot + solved flags).  One warp per parent, 12 children each.
 // Algorithmic bytes per parent: 20 in + 12*(20 + 1920 + 1) out.
 // ---------------------------------------------------------------------------------------------
+template <typename OH>
 __device__ __forceinline__ void warp_expand12(const uint8_t* s_lut, uint32_t v, int lane, int64_t parent,
-                                              int8_t* __restrict__ children, float* __restrict__ children_oh,
+                                              int8_t* __restrict__ children, OH* __restrict__ children_oh,
                                               uint8_t* __restrict__ solved, int pol) {
 #pragma unroll 4
 	for (uint32_t a = 0; a < 12; ++a) {
@@ -322,8 +347,9 @@ __device__ __forceinline__ void warp_expand12(const uint8_t* s_lut, uint32_t v, 
 	}
 }
 
+template <typename OH>
 __global__ void __launch_bounds__(kThreads)
-k_expand12(const int8_t* __restrict__ in, int8_t* __restrict__ children, float* __restrict__ children_oh,
+k_expand12(const int8_t* __restrict__ in, int8_t* __restrict__ children, OH* __restrict__ children_oh,
            uint8_t* __restrict__ solved, int64_t n, int pol) {
 	__shared__ __align__(16) uint8_t s_lut[RB_LUT_BYTES];
 	rb_stage_lut2024(s_lut);
@@ -456,11 +482,11 @@ k_scramble(const uint8_t* __restrict__ actions, int64_t stride_cube, int64_t str
 // state, its one-hot row, its solved flag and (ADI) the 12 children with their one-hot rows and flags.
 // Row index of (game g, position d) is g*depth + d: game-major, depth-minor (cube.py:232).
 // ---------------------------------------------------------------------------------------------
-template <bool kChildren>
+template <bool kChildren, typename OH>
 __global__ void __launch_bounds__(kThreads)
 k_sequence(const uint8_t* __restrict__ faces, const uint8_t* __restrict__ dirs, int games, int depth,
-           int with_solved, int chunk, int8_t* __restrict__ states, float* __restrict__ oh,
-           uint8_t* __restrict__ solved_states, int8_t* __restrict__ children, float* __restrict__ children_oh,
+           int with_solved, int chunk, int8_t* __restrict__ states, OH* __restrict__ oh,
+           uint8_t* __restrict__ solved_states, int8_t* __restrict__ children, OH* __restrict__ children_oh,
            uint8_t* __restrict__ solved_children, int pol) {
 	__shared__ __align__(16) uint8_t s_lut[RB_LUT_BYTES];
 	rb_stage_lut2024(s_lut);

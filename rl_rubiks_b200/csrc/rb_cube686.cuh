@@ -113,12 +113,32 @@ k_is_solved(const int8_t* __restrict__ in, uint8_t* __restrict__ flags, int64_t 
 	}
 }
 
+// Four int8 values (one word) widened to the one-hot element type and stored at element offset 4 * w of `base`:
+// f32 -> one 16-byte store, bf16 (raw bits, every int8 value is exact in bf16) -> one 8-byte store.
+typedef uint16_t rb_bf16;
+__device__ __forceinline__ void store_widened(float* __restrict__ base, int64_t w, uint32_t x, int pol) {
+	float4 o;
+	o.x = (float)(int8_t)(x & 0xff);
+	o.y = (float)(int8_t)((x >> 8) & 0xff);
+	o.z = (float)(int8_t)((x >> 16) & 0xff);
+	o.w = (float)(int8_t)(x >> 24);
+	rb_st_stream(reinterpret_cast<float4*>(base) + w, o, pol);
+}
+__device__ __forceinline__ void store_widened(rb_bf16* __restrict__ base, int64_t w, uint32_t x, int pol) {
+	const uint32_t b0 = __float_as_uint((float)(int8_t)(x & 0xff)) >> 16, b1 = __float_as_uint((float)(int8_t)((x >> 8) & 0xff)) & 0xffff0000u;
+	const uint32_t b2 = __float_as_uint((float)(int8_t)((x >> 16) & 0xff)) >> 16, b3 = __float_as_uint((float)(int8_t)(x >> 24)) & 0xffff0000u;
+	uint2* p = reinterpret_cast<uint2*>(base) + w;
+	const uint2 o = make_uint2(b0 | b1, b2 | b3);
+	if (pol == RB_STORE_CS) __stcs(p, o);
+	else *p = o;
+}
+
 // as_oh: int8 -> f32 widening of the already one-hot state: 288 B in, 1152 B out.  Thread = 4 bytes -> float4, eight
 // independent loads in flight per thread (read latency under a saturating write stream is several microseconds).
+template <typename OH>
 __global__ void __launch_bounds__(kThreads)
-k_as_oh(const int8_t* __restrict__ in, float* __restrict__ oh, int64_t n_words, int pol) {
+k_as_oh(const int8_t* __restrict__ in, OH* __restrict__ oh, int64_t n_words, int pol) {
 	const uint32_t* src = reinterpret_cast<const uint32_t*>(in);
-	float4* dst = reinterpret_cast<float4*>(oh);
 	constexpr int kU = 8;
 	const int64_t step = (int64_t)gridDim.x * blockDim.x * kU;
 	for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x * kU + threadIdx.x; i0 < n_words; i0 += step) {
@@ -127,14 +147,7 @@ k_as_oh(const int8_t* __restrict__ in, float* __restrict__ oh, int64_t n_words, 
 		for (int k = 0; k < kU; ++k) w[k] = i0 + k * kThreads < n_words ? __ldcs(src + i0 + k * kThreads) : 0u;
 #pragma unroll
 		for (int k = 0; k < kU; ++k) {
-			if (i0 + k * kThreads < n_words) {
-				float4 o;
-				o.x = (float)(int8_t)(w[k] & 0xff);
-				o.y = (float)(int8_t)((w[k] >> 8) & 0xff);
-				o.z = (float)(int8_t)((w[k] >> 16) & 0xff);
-				o.w = (float)(int8_t)(w[k] >> 24);
-				rb_st_stream(dst + i0 + k * kThreads, o, pol);
-			}
+			if (i0 + k * kThreads < n_words) store_widened(oh, i0 + k * kThreads, w[k], pol);
 		}
 	}
 }
@@ -157,24 +170,16 @@ k_as_correct(const float* __restrict__ oh, float* __restrict__ out, int64_t n_sl
 }
 
 // Emit one state held in shared memory (288 B at `s`): raw bytes, f32 one-hot row and solved flag; warp-wide.
+template <typename OH>
 __device__ __forceinline__ void warp_emit(const uint8_t* s, int lane, int64_t row, int8_t* __restrict__ states,
-                                          float* __restrict__ oh, uint8_t* __restrict__ solved, int pol) {
+                                          OH* __restrict__ oh, uint8_t* __restrict__ solved, int pol) {
 	if (states && lane < 18)
 		rb_st_stream(reinterpret_cast<uint4*>(states + row * kStateBytes) + lane, reinterpret_cast<const uint4*>(s)[lane], pol);
 	if (oh) {
-		float4* dst = reinterpret_cast<float4*>(oh + row * kStateBytes);
 #pragma unroll
 		for (int k = 0; k < 3; ++k) {
 			const int w = lane + 32 * k;
-			if (w < 72) {
-				const uint32_t x = reinterpret_cast<const uint32_t*>(s)[w];
-				float4 o;
-				o.x = (float)(int8_t)(x & 0xff);
-				o.y = (float)(int8_t)((x >> 8) & 0xff);
-				o.z = (float)(int8_t)((x >> 16) & 0xff);
-				o.w = (float)(int8_t)(x >> 24);
-				rb_st_stream(dst + w, o, pol);
-			}
+			if (w < 72) store_widened(oh + row * kStateBytes, w, reinterpret_cast<const uint32_t*>(s)[w], pol);
 		}
 	}
 	if (solved) {
@@ -199,8 +204,9 @@ __device__ __forceinline__ void warp_move(uint8_t* dst, const uint8_t* src, cons
 constexpr int kWarps = kThreads / 32;
 
 // expand12 (+ one-hot + solved): warp per parent; parent and one child buffer per warp in shared memory.
+template <typename OH>
 __device__ __forceinline__ void warp_expand12(uint8_t* child, const uint8_t* parent, const uint8_t* s_perm, int lane,
-                                              int64_t prow, int8_t* __restrict__ children, float* __restrict__ children_oh,
+                                              int64_t prow, int8_t* __restrict__ children, OH* __restrict__ children_oh,
                                               uint8_t* __restrict__ solved, int pol) {
 	for (uint32_t a = 0; a < 12; ++a) {
 		warp_move(child, parent, s_perm, a, lane);
@@ -209,8 +215,9 @@ __device__ __forceinline__ void warp_expand12(uint8_t* child, const uint8_t* par
 	}
 }
 
+template <typename OH>
 __global__ void __launch_bounds__(kThreads)
-k_expand12(const int8_t* __restrict__ in, int8_t* __restrict__ children, float* __restrict__ children_oh,
+k_expand12(const int8_t* __restrict__ in, int8_t* __restrict__ children, OH* __restrict__ children_oh,
            uint8_t* __restrict__ solved, int64_t n, int pol) {
 	__shared__ __align__(16) uint8_t s_perm[12 * 48];
 	__shared__ __align__(16) uint8_t s_buf[kWarps][2][kStateBytes];
@@ -332,11 +339,11 @@ k_render_from2024(int8_t* __restrict__ io, const int8_t* __restrict__ start, int
 }
 
 // sequence_scramble / fused ADI generator: same unit decomposition as the 20x24 kernel (game, chunk of depth).
-template <bool kChildren>
+template <bool kChildren, typename OH>
 __global__ void __launch_bounds__(kThreads)
 k_sequence(const uint8_t* __restrict__ faces, const uint8_t* __restrict__ dirs, int games, int depth,
-           int with_solved, int chunk, int8_t* __restrict__ states, float* __restrict__ oh,
-           uint8_t* __restrict__ solved_states, int8_t* __restrict__ children, float* __restrict__ children_oh,
+           int with_solved, int chunk, int8_t* __restrict__ states, OH* __restrict__ oh,
+           uint8_t* __restrict__ solved_states, int8_t* __restrict__ children, OH* __restrict__ children_oh,
            uint8_t* __restrict__ solved_children, int pol) {
 	__shared__ __align__(16) uint8_t s_perm[12 * 48];
 	__shared__ __align__(16) uint8_t s_buf[kWarps][3][kStateBytes];

@@ -110,25 +110,32 @@ int rb_multi_is_solved(int rep, const int8_t* states, uint8_t* flags, int64_t n,
 	return RB_OK;
 }
 
-int rb_as_oh(int rep, const int8_t* states, float* oh, int64_t n, rb_stream_t stream) {
+// OH = float (the reference's one-hot dtype) or rb_bf16 (raw bfloat16 bits: the same 0/1 values, half the bytes)
+extern "C++" {
+template <typename OH>
+static int as_oh_impl(int rep, const int8_t* states, OH* oh, int64_t n, rb_stream_t stream) {
 	RB_REQUIRE(rep_ok(rep) && n >= 0, "bad rep or size");
 	if (n == 0) return RB_OK;
 	RB_REQUIRE(states && oh, "null pointer");
 	RB_REQUIRE(aligned(oh, 16), "one-hot output must be 16-byte aligned");
 	RB_INIT();
+	const int64_t esz = sizeof(OH);
 	if (rep == RB_REP_2024) {
 		if (aligned(states, 4))
-			rb2024::k_as_oh<<<rb_grid(n, rb2024::kThreads, 6), rb2024::kThreads, 0, S(stream)>>>(states, oh, n, rb_store_policy(n * 1920));
+			rb2024::k_as_oh<OH><<<rb_grid(n, rb2024::kThreads, 6), rb2024::kThreads, 0, S(stream)>>>(states, oh, n, rb_store_policy(n * 480 * esz));
 		else
-			rb2024::k_as_oh_any<<<rb_grid(n, 8, 8), rb2024::kThreads, 0, S(stream)>>>(states, oh, n, rb_store_policy(n * 1920));
+			rb2024::k_as_oh_any<OH><<<rb_grid(n, 8, 8), rb2024::kThreads, 0, S(stream)>>>(states, oh, n, rb_store_policy(n * 480 * esz));
 		RB_LAUNCHED("as_oh_2024");
 	} else {
 		RB_REQUIRE(aligned(states, 4), "6x8x6 states must be 4-byte aligned");
-		rb686::k_as_oh<<<rb_grid(n * 72, rb686::kThreads * 8, 8), rb686::kThreads, 0, S(stream)>>>(states, oh, n * 72, rb_store_policy(n * 1152));
+		rb686::k_as_oh<OH><<<rb_grid(n * 72, rb686::kThreads * 8, 8), rb686::kThreads, 0, S(stream)>>>(states, oh, n * 72, rb_store_policy(n * 288 * esz));
 		RB_LAUNCHED("as_oh_686");
 	}
 	return RB_OK;
 }
+}  // extern "C++"
+int rb_as_oh(int rep, const int8_t* states, float* oh, int64_t n, rb_stream_t stream) { return as_oh_impl<float>(rep, states, oh, n, stream); }
+int rb_as_oh_bf16(int rep, const int8_t* states, uint16_t* oh, int64_t n, rb_stream_t stream) { return as_oh_impl<uint16_t>(rep, states, oh, n, stream); }
 
 int rb_as_correct_686(const float* oh, float* out, int64_t n, rb_stream_t stream) {
 	RB_REQUIRE(n >= 0, "bad size");
@@ -140,8 +147,11 @@ int rb_as_correct_686(const float* oh, float* out, int64_t n, rb_stream_t stream
 	return RB_OK;
 }
 
-int rb_expand12(int rep, const int8_t* states, int8_t* children, float* children_oh, uint8_t* solved, int64_t n,
-                rb_stream_t stream) {
+extern "C++" {
+template <typename OH>
+static int expand12_impl(int rep, const int8_t* states, int8_t* children, OH* children_oh, uint8_t* solved, int64_t n,
+                         rb_stream_t stream) {
+	const int64_t esz = sizeof(OH);
 	RB_REQUIRE(rep_ok(rep) && n >= 0, "bad rep or size");
 	if (n == 0) return RB_OK;
 	RB_REQUIRE(states && (children || children_oh || solved), "null pointer");
@@ -151,19 +161,26 @@ int rb_expand12(int rep, const int8_t* states, int8_t* children, float* children
 		if (!children_oh && aligned(states, 4) && aligned(children, 16) && aligned(solved, 4))
 			rb2024::k_expand12_states<<<rb_grid(n, rb2024::kExpThreads, 5), rb2024::kExpThreads, 0, S(stream)>>>(states, children, solved, n, rb_store_policy(n * 240));
 		else
-			rb2024::k_expand12<<<rb_grid(n, 8, 8), rb2024::kThreads, 0, S(stream)>>>(states, children, children_oh, solved, n,
-			                                                                             rb_store_policy(children_oh ? n * 12 * 1920 : n * 240));
+			rb2024::k_expand12<OH><<<rb_grid(n, 8, 8), rb2024::kThreads, 0, S(stream)>>>(states, children, children_oh, solved, n,
+			                                                                                 rb_store_policy(children_oh ? n * 12 * 480 * esz : n * 240));
 		RB_LAUNCHED("expand12_2024");
 	} else {
 		RB_REQUIRE(aligned(states, 16) && aligned(children, 16), "6x8x6 states must be 16-byte aligned");
 		if (!children_oh && !solved)
 			rb686::k_expand12_states<<<rb_grid(n, rb686::kWarps, 8), rb686::kThreads, 0, S(stream)>>>(states, children, n);
 		else
-			rb686::k_expand12<<<rb_grid(n, rb686::kWarps, 6), rb686::kThreads, 0, S(stream)>>>(states, children, children_oh, solved, n,
-			                                                                                 rb_store_policy(n * 12 * (children_oh ? 1440 : 288)));
+			rb686::k_expand12<OH><<<rb_grid(n, rb686::kWarps, 6), rb686::kThreads, 0, S(stream)>>>(states, children, children_oh, solved, n,
+			                                                                                     rb_store_policy(n * 12 * (children_oh ? 288 * (esz + 1) : 288)));
 		RB_LAUNCHED("expand12_686");
 	}
 	return RB_OK;
+}
+}  // extern "C++"
+int rb_expand12(int rep, const int8_t* states, int8_t* children, float* children_oh, uint8_t* solved, int64_t n, rb_stream_t stream) {
+	return expand12_impl<float>(rep, states, children, children_oh, solved, n, stream);
+}
+int rb_expand12_bf16(int rep, const int8_t* states, int8_t* children, uint16_t* children_oh, uint8_t* solved, int64_t n, rb_stream_t stream) {
+	return expand12_impl<uint16_t>(rep, states, children, children_oh, solved, n, stream);
 }
 
 int rb_scramble(int rep, const uint8_t* actions, int64_t stride_cube, int64_t stride_move, const int8_t* start,
@@ -211,9 +228,12 @@ static int sequence_chunk(int64_t games, int depth) {
 	return (int)((depth + chunks_per_game - 1) / chunks_per_game);
 }
 
+extern "C++" {
+template <typename OH>
 static int launch_sequence(int rep, bool with_children, const uint8_t* faces, const uint8_t* dirs, int32_t games,
-                           int32_t depth, int32_t with_solved, int8_t* states, float* oh, uint8_t* solved_states,
-                           int8_t* children, float* children_oh, uint8_t* solved_children, rb_stream_t stream) {
+                           int32_t depth, int32_t with_solved, int8_t* states, OH* oh, uint8_t* solved_states,
+                           int8_t* children, OH* children_oh, uint8_t* solved_children, rb_stream_t stream) {
+	const int64_t esz = sizeof(OH);
 	RB_REQUIRE(rep_ok(rep) && games >= 0 && depth >= 0, "bad rep or size");
 	if (games == 0 || depth == 0) return RB_OK;
 	RB_REQUIRE(faces || (depth == 1 && with_solved), "null action pointer");
@@ -223,7 +243,7 @@ static int launch_sequence(int rep, bool with_children, const uint8_t* faces, co
 	const int chunk = sequence_chunk(games, depth);
 	const int64_t units = (int64_t)games * ((depth + chunk - 1) / chunk);
 	const int64_t rows = (int64_t)games * depth * (with_children ? 13 : 1);
-	const int pol = rb_store_policy(rows * (rep == RB_REP_2024 ? ((oh || children_oh) ? 1920 : 20) : ((oh || children_oh) ? 1440 : 288)));
+	const int pol = rb_store_policy(rows * (rep == RB_REP_2024 ? ((oh || children_oh) ? 480 * esz : 20) : ((oh || children_oh) ? 288 * (esz + 1) : 288)));
 	if (rep == RB_REP_2024 && !with_children && !oh && aligned(states, 4)) {
 		// states / flags only: thread per game, register LUT, staged coalesced output
 		rb2024::k_sequence_states<<<rb_grid(games, rb2024::kThreads, 4), rb2024::kThreads, 0, S(stream)>>>(faces, dirs, games, depth, ws,
@@ -232,36 +252,47 @@ static int launch_sequence(int rep, bool with_children, const uint8_t* faces, co
 	} else if (rep == RB_REP_2024) {
 		const int grid = rb_grid(units, 8, 8);
 		if (with_children)
-			rb2024::k_sequence<true><<<grid, rb2024::kThreads, 0, S(stream)>>>(faces, dirs, games, depth, ws, chunk, states, oh,
-			                                                               solved_states, children, children_oh, solved_children, pol);
+			rb2024::k_sequence<true, OH><<<grid, rb2024::kThreads, 0, S(stream)>>>(faces, dirs, games, depth, ws, chunk, states, oh,
+			                                                                   solved_states, children, children_oh, solved_children, pol);
 		else
-			rb2024::k_sequence<false><<<grid, rb2024::kThreads, 0, S(stream)>>>(faces, dirs, games, depth, ws, chunk, states, oh,
-			                                                                solved_states, nullptr, nullptr, nullptr, pol);
+			rb2024::k_sequence<false, OH><<<grid, rb2024::kThreads, 0, S(stream)>>>(faces, dirs, games, depth, ws, chunk, states, oh,
+			                                                                    solved_states, nullptr, (OH*)nullptr, nullptr, pol);
 		RB_LAUNCHED("sequence_2024");
 	} else {
 		RB_REQUIRE(aligned(states, 16) && aligned(children, 16), "6x8x6 states must be 16-byte aligned");
 		const int grid = rb_grid(units, rb686::kWarps, 6);
 		if (with_children)
-			rb686::k_sequence<true><<<grid, rb686::kThreads, 0, S(stream)>>>(faces, dirs, games, depth, ws, chunk, states, oh,
-			                                                              solved_states, children, children_oh, solved_children, pol);
+			rb686::k_sequence<true, OH><<<grid, rb686::kThreads, 0, S(stream)>>>(faces, dirs, games, depth, ws, chunk, states, oh,
+			                                                                  solved_states, children, children_oh, solved_children, pol);
 		else
-			rb686::k_sequence<false><<<grid, rb686::kThreads, 0, S(stream)>>>(faces, dirs, games, depth, ws, chunk, states, oh,
-			                                                               solved_states, nullptr, nullptr, nullptr, pol);
+			rb686::k_sequence<false, OH><<<grid, rb686::kThreads, 0, S(stream)>>>(faces, dirs, games, depth, ws, chunk, states, oh,
+			                                                                   solved_states, nullptr, (OH*)nullptr, nullptr, pol);
 		RB_LAUNCHED("sequence_686");
 	}
 	return RB_OK;
 }
+}  // extern "C++"
 
 int rb_sequence_scramble(int rep, const uint8_t* faces, const uint8_t* dirs, int32_t games, int32_t depth,
                          int32_t with_solved, int8_t* states, float* oh, uint8_t* solved, rb_stream_t stream) {
-	return launch_sequence(rep, false, faces, dirs, games, depth, with_solved, states, oh, solved, nullptr, nullptr, nullptr, stream);
+	return launch_sequence<float>(rep, false, faces, dirs, games, depth, with_solved, states, oh, solved, nullptr, nullptr, nullptr, stream);
+}
+int rb_sequence_scramble_bf16(int rep, const uint8_t* faces, const uint8_t* dirs, int32_t games, int32_t depth,
+                              int32_t with_solved, int8_t* states, uint16_t* oh, uint8_t* solved, rb_stream_t stream) {
+	return launch_sequence<uint16_t>(rep, false, faces, dirs, games, depth, with_solved, states, oh, solved, nullptr, nullptr, nullptr, stream);
 }
 
 int rb_adi_generate(int rep, const uint8_t* faces, const uint8_t* dirs, int32_t games, int32_t depth, int32_t with_solved,
                     int8_t* states, float* oh_states, int8_t* children, float* children_oh, uint8_t* solved_states,
                     uint8_t* solved_children, rb_stream_t stream) {
-	return launch_sequence(rep, true, faces, dirs, games, depth, with_solved, states, oh_states, solved_states, children,
-	                       children_oh, solved_children, stream);
+	return launch_sequence<float>(rep, true, faces, dirs, games, depth, with_solved, states, oh_states, solved_states, children,
+	                              children_oh, solved_children, stream);
+}
+int rb_adi_generate_bf16(int rep, const uint8_t* faces, const uint8_t* dirs, int32_t games, int32_t depth, int32_t with_solved,
+                         int8_t* states, uint16_t* oh_states, int8_t* children, uint16_t* children_oh, uint8_t* solved_states,
+                         uint8_t* solved_children, rb_stream_t stream) {
+	return launch_sequence<uint16_t>(rep, true, faces, dirs, games, depth, with_solved, states, oh_states, solved_states, children,
+	                                 children_oh, solved_children, stream);
 }
 
 static int adi_targets_impl(const float* values, const uint8_t* solved_children, const uint8_t* solved_states, int64_t n,

@@ -213,11 +213,21 @@ def is_solved(state) -> bool:
 
 
 # ---- one-hot (cube.py:130-140, 265-277, 363-380) ---------------------------------------------------
-def as_oh(states) -> torch.Tensor:
-	"""n states -> f32 (n, 480 | 288) on the GPU; a single state gives a leading dimension of 1."""
+def _oh_fn(name: str, dtype):
+	"""The f32 entry point (the reference's one-hot dtype) or its bfloat16 variant (opt-in: same 0/1 values, half the bytes)."""
+	if dtype == torch.float32:
+		return getattr(N.lib, name)
+	if dtype == torch.bfloat16:
+		return getattr(N.lib, name + "_bf16")
+	raise TypeError(f"one-hot dtype must be torch.float32 or torch.bfloat16, got {dtype}")
+
+
+def as_oh(states, dtype=torch.float32) -> torch.Tensor:
+	"""n states -> f32 (n, 480 | 288) on the GPU; a single state gives a leading dimension of 1.  `dtype=torch.bfloat16`
+	(not in the reference) emits the same rows as bf16 for a bf16 forward of the net."""
 	s, _, _ = _states_in(states)
-	oh = torch.empty(s.shape[0], get_oh_shape(), dtype=torch.float32, device=s.device)
-	N.check(N.lib.rb_as_oh(_rep(), N.ptr(s), N.ptr(oh), s.shape[0], N.stream_handle()))
+	oh = torch.empty(s.shape[0], get_oh_shape(), dtype=dtype, device=s.device)
+	N.check(_oh_fn("rb_as_oh", dtype)(_rep(), N.ptr(s), N.ptr(oh), s.shape[0], N.stream_handle()))
 	return oh
 
 
@@ -262,16 +272,16 @@ def rev_actions(actions):
 	return rev
 
 
-def expand12(states, with_oh: bool = False, with_solved: bool = False):
+def expand12(states, with_oh: bool = False, with_solved: bool = False, oh_dtype=torch.float32):
 	"""The 12-neighbour expansion `multi_rotate(np.repeat(S, 12, 0), *iter_actions(len(S)))` (train.py:285,
 	agents.py:277-281) as one fused kernel: child i*12+a = action a on state i.  Optionally also returns the
 	children's one-hot (f32 CUDA tensor) and solved flags from the same launch."""
 	s, was_np, _ = _states_in(states)
 	n = s.shape[0]
 	children = torch.empty(12 * n, *shape(), dtype=torch.int8, device=s.device)
-	oh = torch.empty(12 * n, get_oh_shape(), dtype=torch.float32, device=s.device) if with_oh else None
+	oh = torch.empty(12 * n, get_oh_shape(), dtype=oh_dtype, device=s.device) if with_oh else None
 	flags = torch.empty(12 * n, dtype=torch.uint8, device=s.device) if with_solved else None
-	N.check(N.lib.rb_expand12(_rep(), N.ptr(s), N.ptr(children), N.ptr(oh), N.ptr(flags), n, N.stream_handle()))
+	N.check(_oh_fn("rb_expand12", oh_dtype)(_rep(), N.ptr(s), N.ptr(children), N.ptr(oh), N.ptr(flags), n, N.stream_handle()))
 	res = [_out(children, was_np)]
 	if with_oh:
 		res.append(oh)
@@ -318,7 +328,7 @@ def scramble(depth: int, force_not_solved=False):
 
 
 def sequence_scrambler_from(faces, dirs, with_solved: bool, device_out: bool = False, with_oh: bool = True,
-							with_flags: bool = False):
+							with_flags: bool = False, oh_dtype=torch.float32):
 	"""`sequence_scrambler` with the (depth, games) draws supplied by the caller.  `with_oh=False` skips the one-hot
 	(states-only fast kernel); `with_flags` also returns the solved flag of every emitted state."""
 	faces, dirs = np.asarray(faces), np.asarray(dirs)
@@ -326,9 +336,9 @@ def sequence_scrambler_from(faces, dirs, with_solved: bool, device_out: bool = F
 	a = torch.from_numpy(_actions_u8(faces, dirs)).to(_dev())
 	n = games * depth
 	states = torch.empty(n, *shape(), dtype=torch.int8, device=a.device)
-	oh = torch.empty(n, get_oh_shape(), dtype=torch.float32, device=a.device) if with_oh else None
+	oh = torch.empty(n, get_oh_shape(), dtype=oh_dtype, device=a.device) if with_oh else None
 	flags = torch.empty(n, dtype=torch.uint8, device=a.device) if with_flags else None
-	N.check(N.lib.rb_sequence_scramble(_rep(), N.ptr(a), None, games, depth, int(bool(with_solved)), N.ptr(states), N.ptr(oh),
+	N.check(_oh_fn("rb_sequence_scramble", oh_dtype)(_rep(), N.ptr(a), None, games, depth, int(bool(with_solved)), N.ptr(states), N.ptr(oh),
 									   N.ptr(flags), N.stream_handle()))
 	res = [states if device_out else states.cpu().numpy(), oh]
 	if with_flags:

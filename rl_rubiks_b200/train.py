@@ -37,7 +37,7 @@ class Train:
 	def __init__(self, rollouts: int, batch_size: int, rollout_games: int, rollout_depth: int, optim_fn, alpha_update: float,
 				 lr: float, gamma: float, update_interval: int, tau: float, reward_method: str, agent=None, evaluator=None,
 				 evaluation_interval: int = 0, policy_criterion=torch.nn.CrossEntropyLoss, value_criterion=torch.nn.MSELoss,
-				 data_parallel: bool = False, log=None):
+				 data_parallel: bool = False, log=None, oh_dtype=torch.float32):
 		N.require_cuda()
 		self.rollouts = int(rollouts)
 		self.train_rollouts = np.arange(self.rollouts)
@@ -53,6 +53,8 @@ class Train:
 		self.policy_criterion = policy_criterion(reduction="none")
 		self.value_criterion = value_criterion(reduction="none")
 		self.data_parallel = bool(data_parallel)
+		# torch.bfloat16 (not in the reference): one-hot batches are emitted as bf16 and every forward runs under bf16 autocast
+		self.oh_dtype = oh_dtype
 		self.log = log or (lambda *a, **k: None)
 		self.alphas, self.lrs = [], []
 
@@ -92,13 +94,14 @@ class Train:
 
 	def ADI_traindata(self, net, alpha: float):
 		"""train.py:256-339 on the device (rl_rubiks_b200.adi): (oh_states, policy_targets, value_targets, loss_weights)."""
-		return adi.adi_traindata(net, self.rollout_games, self.rollout_depth, self.reward_method, alpha,
-								 ff_batches=self.adi_ff_batches, generator=self._generator)
+		with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.oh_dtype == torch.bfloat16):
+			return adi.adi_traindata(net, self.rollout_games, self.rollout_depth, self.reward_method, alpha,
+									 ff_batches=self.adi_ff_batches, generator=self._generator)
 
 	def train(self, net):
 		"""Returns (net after the last rollout, net with the best evaluation score), as train.py:111-247."""
 		dev = torch.device("cuda", torch.cuda.current_device())
-		self._generator = adi.ADIGenerator(self.rollout_games, self.rollout_depth, self.reward_method)
+		self._generator = adi.ADIGenerator(self.rollout_games, self.rollout_depth, self.reward_method, oh_dtype=self.oh_dtype)
 		best_solve, best_net = 0, _clone(net)
 		if self.agent is not None:
 			self.agent.net = net
@@ -123,7 +126,9 @@ class Train:
 			acc.zero_()
 			for batch in batches:
 				optimizer.zero_grad()
-				policy_pred, value_pred = net(training_data[batch], policy=True, value=True)
+				with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.oh_dtype == torch.bfloat16):
+					policy_pred, value_pred = net(training_data[batch], policy=True, value=True)
+				policy_pred, value_pred = policy_pred.float(), value_pred.float()
 				policy_loss = self.policy_criterion(policy_pred, policy_targets[batch]) * loss_weights[batch]
 				value_loss = self.value_criterion(value_pred.squeeze(), value_targets[batch]) * loss_weights[batch]
 				loss = torch.mean(policy_loss + value_loss)

@@ -54,7 +54,9 @@ def main():
 	ap.add_argument("--batch", type=int, default=1000)
 	ap.add_argument("--ff-batches", type=int, default=4, help="slices of the value-net forward over the children (train.py:249-254)")
 	ap.add_argument("--tf32", action="store_true")
+	ap.add_argument("--bf16", action="store_true", help="bf16 one-hot batches + bf16 autocast forward (opt-in, not the reference's dtype)")
 	args = ap.parse_args()
+	oh_dtype = torch.bfloat16 if args.bf16 else torch.float32
 	rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 	torch.cuda.set_device(local)
 	dev = torch.device("cuda", local)
@@ -68,13 +70,16 @@ def main():
 	games = hi - lo
 
 	# (a) generation alone: kernels + value-net forward + targets
-	g = adi.ADIGenerator(games, args.depth, "lapanfix")
+	g = adi.ADIGenerator(games, args.depth, "lapanfix", oh_dtype=oh_dtype)
+	cast = torch.autocast("cuda", dtype=torch.bfloat16, enabled=args.bf16)
 	for _ in range(2):
-		adi.adi_traindata(net, games, args.depth, "lapanfix", 0.5, ff_batches=args.ff_batches, generator=g)
+		with cast:
+			adi.adi_traindata(net, games, args.depth, "lapanfix", 0.5, ff_batches=args.ff_batches, generator=g)
 	torch.cuda.synchronize()
 	t0 = time.perf_counter()
 	for _ in range(args.rollouts):
-		adi.adi_traindata(net, games, args.depth, "lapanfix", 0.5, ff_batches=args.ff_batches, generator=g)
+		with cast:
+			adi.adi_traindata(net, games, args.depth, "lapanfix", 0.5, ff_batches=args.ff_batches, generator=g)
 	torch.cuda.synchronize()
 	gen_s = (time.perf_counter() - t0) / args.rollouts
 	# kernels only (no net): generate + targets on stale values
@@ -89,7 +94,7 @@ def main():
 
 	# (b) the whole loop: generation + SGD over the rollout's minibatches
 	t = Train(rollouts=args.rollouts + 1, batch_size=args.batch, rollout_games=games, rollout_depth=args.depth, optim_fn=torch.optim.Adam,
-			  alpha_update=0.5, lr=1e-5, gamma=1, update_interval=1, tau=1, reward_method="lapanfix", data_parallel=world > 1)
+			  alpha_update=0.5, lr=1e-5, gamma=1, update_interval=1, tau=1, reward_method="lapanfix", data_parallel=world > 1, oh_dtype=oh_dtype)
 	t.adi_ff_batches = args.ff_batches
 	marks = []
 	t.log = lambda *_: (torch.cuda.synchronize(), marks.append(time.perf_counter()))
@@ -102,7 +107,7 @@ def main():
 	if rank == 0:
 		n = args.games * args.depth
 		print(f"gpus {world} games {args.games} depth {args.depth} ({n} samples, {12 * n} children per rollout) batch {args.batch} "
-			  f"{'tf32' if args.tf32 else 'fp32'} net fc_small:")
+			  f"{'bf16 one-hot + autocast' if args.bf16 else ('tf32' if args.tf32 else 'fp32')} net fc_small:")
 		print(f"  ADI kernels only        : {stats['ker'] * 1e3:9.3f} ms / rollout = {n / stats['ker'] / 1e6:9.2f} M samples/s")
 		print(f"  ADI incl. value forward : {stats['gen'] * 1e3:9.3f} ms / rollout = {n / stats['gen'] / 1e6:9.2f} M samples/s")
 		print(f"  ADI + SGD (Train.train) : {stats['loop'] * 1e3:9.3f} ms / rollout = {n / stats['loop'] / 1e6:9.2f} M samples/s  "
