@@ -307,34 +307,76 @@ k_render_from2024(int8_t* __restrict__ io, const int8_t* __restrict__ start, int
 		reinterpret_cast<uint32_t*>(s_tab)[i] = reinterpret_cast<const uint32_t*>(g_stickers686)[i];
 	__syncthreads();
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-	for (int64_t i = (int64_t)blockIdx.x * kWarps + wib; i < n; i += (int64_t)gridDim.x * kWarps) {
-		int8_t* row = io + i * kStateBytes;
-		const uint32_t v = lane < 20 ? (uint32_t)(uint8_t)row[lane] : 0u;
-		if (start && lane < 18) reinterpret_cast<uint4*>(s_src[wib])[lane] = rb_ld_stream(reinterpret_cast<const uint4*>(start + i * kStateBytes) + lane);
-		__syncwarp();
+	const int64_t stride = (int64_t)gridDim.x * kWarps;
+	// Per-lane constants of its two stickers j = lane, lane + 32 (24 corner stickers, then 24 edge stickers): owning cubie,
+	// table row base, home slot (source record) and, for a solved start, the record itself (one-hot of the home face's colour).
+	int cub[2], tab[2], srcoff[2];
+	uint16_t solved_rec[2][3];
 #pragma unroll
-		for (int r = 0; r < 2; ++r) {
-			const int j = lane + 32 * r;                           // sticker index: 24 corner stickers, then 24 edge stickers
-			const int c = j < 24 ? j / 3 : 8 + ((j - 24) >> 1), k = j < 24 ? j - 3 * (j / 3) : (j - 24) & 1;
-			uint32_t val = __shfl_sync(0xffffffffu, v, c < 20 ? c : 0);
-			if (j < 48) {
-				val = val < 24u ? val : 0u;
-				const uint32_t dst = s_tab[(c * 24 + val) * 3 + k], src = s_tab[kStickerDst + c * 3 + k];
-				uint16_t h0, h1, h2;
-				if (start) {
-					const uint16_t* q = reinterpret_cast<const uint16_t*>(s_src[wib] + src * 6);
-					h0 = q[0]; h1 = q[1]; h2 = q[2];
-				} else {                                           // solved start: one-hot of the home face's colour
-					const uint32_t face = src >> 3, bit = 1u << (8 * (face & 1u));
-					h0 = (uint16_t)((face >> 1) == 0 ? bit : 0); h1 = (uint16_t)((face >> 1) == 1 ? bit : 0); h2 = (uint16_t)((face >> 1) == 2 ? bit : 0);
-				}
-				uint16_t* o = reinterpret_cast<uint16_t*>(s_out[wib] + dst * 6);
-				o[0] = h0; o[1] = h1; o[2] = h2;
-			}
+	for (int r = 0; r < 2; ++r) {
+		const int j = lane + 32 * r;
+		const int c = j < 24 ? j / 3 : 8 + ((j - 24) >> 1), k = j < 24 ? j - 3 * (j / 3) : (j - 24) & 1;
+		cub[r] = c < 20 ? c : 0;
+		tab[r] = c * 72 + k;
+		const uint32_t src = j < 48 ? s_tab[kStickerDst + c * 3 + k] : 0u;
+		srcoff[r] = (int)src * 6;
+		const uint32_t face = src >> 3, bit = 1u << (8 * (face & 1u));
+#pragma unroll
+		for (int h = 0; h < 3; ++h) solved_rec[r][h] = (uint16_t)((face >> 1) == (uint32_t)h ? bit : 0u);
+	}
+	// Work unit = 32 consecutive cubes per warp.  Read latency under a saturating write stream is several microseconds, so the
+	// parked 20x24 states of the warp's NEXT 32 cubes (lane l: the 20 bytes of cube l) are fetched into registers while the
+	// current 32 are rendered from shared memory; the start row (if any) is fetched one cube ahead.
+	__shared__ __align__(16) uint32_t s_park[kWarps][32 * 5];
+	const int64_t n_chunks = (n + 31) / 32;
+	int64_t ch = (int64_t)blockIdx.x * kWarps + wib;
+	uint32_t pk[5] = {0u, 0u, 0u, 0u, 0u};
+	auto fetch_parked = [&](int64_t c) {
+		const int64_t cube = c * 32 + lane;
+		if (c < n_chunks && cube < n) {
+			const uint4 q = *reinterpret_cast<const uint4*>(io + cube * kStateBytes);
+			pk[0] = q.x; pk[1] = q.y; pk[2] = q.z; pk[3] = q.w;
+			pk[4] = *reinterpret_cast<const uint32_t*>(io + cube * kStateBytes + 16);
 		}
+	};
+	uint4 src_next = make_uint4(0u, 0u, 0u, 0u);
+	auto fetch_start = [&](int64_t cube) {
+		if (start && cube < n && lane < 18) src_next = rb_ld_stream(reinterpret_cast<const uint4*>(start + cube * kStateBytes) + lane);
+	};
+	fetch_parked(ch);
+	for (; ch < n_chunks; ch += stride) {
+		const int64_t base = ch * 32;
+		const int cnt = (int)min((int64_t)32, n - base);
+#pragma unroll
+		for (int k = 0; k < 5; ++k) s_park[wib][lane * 5 + k] = pk[k];
+		fetch_parked(ch + stride);
+		fetch_start(base);
 		__syncwarp();
-		if (lane < 18) rb_st_stream(reinterpret_cast<uint4*>(row) + lane, reinterpret_cast<const uint4*>(s_out[wib])[lane], RB_STORE_CS);
-		__syncwarp();
+		for (int t = 0; t < cnt; ++t) {
+			int8_t* row = io + (base + t) * kStateBytes;
+			const uint32_t v = lane < 20 ? (uint32_t)reinterpret_cast<const uint8_t*>(s_park[wib])[t * 20 + lane] : 0u;
+			if (start && lane < 18) reinterpret_cast<uint4*>(s_src[wib])[lane] = src_next;
+			if (t + 1 < cnt) fetch_start(base + t + 1);
+			__syncwarp();
+#pragma unroll
+			for (int r = 0; r < 2; ++r) {
+				uint32_t val = __shfl_sync(0xffffffffu, v, cub[r]);
+				if (lane + 32 * r < 48) {
+					val = val < 24u ? val : 0u;
+					const uint32_t dst = s_tab[tab[r] + val * 3];
+					uint16_t h0 = solved_rec[r][0], h1 = solved_rec[r][1], h2 = solved_rec[r][2];
+					if (start) {
+						const uint16_t* q = reinterpret_cast<const uint16_t*>(s_src[wib] + srcoff[r]);
+						h0 = q[0]; h1 = q[1]; h2 = q[2];
+					}
+					uint16_t* o = reinterpret_cast<uint16_t*>(s_out[wib] + dst * 6);
+					o[0] = h0; o[1] = h1; o[2] = h2;
+				}
+			}
+			__syncwarp();
+			if (lane < 18) rb_st_stream(reinterpret_cast<uint4*>(row) + lane, reinterpret_cast<const uint4*>(s_out[wib])[lane], RB_STORE_CS);
+			__syncwarp();
+		}
 	}
 }
 

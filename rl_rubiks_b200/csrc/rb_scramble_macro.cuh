@@ -476,9 +476,14 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 		if ((int)lane < cnt) {
 			uint8_t* row = buf + lane * depth;
 			Slots s{0x60402000u, 0xe0c0a080u, 0x03020100u, 0x07060504u, 0x0b0a0908u};
+			// depth % 4 != 0: rows start at any byte; two aligned words and one funnel shift give the four action bytes at m
+			// (m is a multiple of 4 here; the word after the row's last one may belong to the next row or to the 16 bytes of
+			// slack behind the last buffer)
+			const uint32_t* arow = reinterpret_cast<const uint32_t*>(buf + ((lane * depth) & ~3));
+			const uint32_t ashift = ((lane * depth) & 3) * 8;
 			auto word_at = [&](int m) -> uint32_t {
 				if (kWordAligned) return *reinterpret_cast<const uint32_t*>(row + m);
-				return row[m] | (row[m + 1] << 8) | (row[m + 2] << 16) | ((uint32_t)row[m + 3] << 24);
+				return __funnelshift_r(arow[m >> 2], arow[(m >> 2) + 1], ashift);
 			};
 			auto apply3 = [&](uint32_t r) {
 				const uint32_t o1 = mad_u32(r, 16u * kRep1, off1), o2 = mad_u32(r, 4u * R2, off2);
@@ -592,7 +597,7 @@ static int warps_for(int64_t n, int depth) {
 static int64_t fixed_smem3(int r2) { return (int64_t)kP1Bytes3 + (int64_t)kP2Rows3 * 4 * r2 + kTailBytes + kMaxThreads / 32 * 8; }
 static int warps_for3(int64_t n, int depth, int r2) {
 	if (depth < 20) return 0;
-	int64_t w = (kSmemBudget - fixed_smem3(r2)) / (32 * (int64_t)depth);
+	int64_t w = (kSmemBudget - 16 - fixed_smem3(r2)) / (32 * (int64_t)depth);
 	if (w > max_threads() / 32) w = max_threads() / 32;
 	if (w < 8) return 0;                         // long sequences: too few resident warps to hide the table latency
 	const int64_t spread = ((n + 31) / 32 + RB_NUM_SMS - 1) / RB_NUM_SMS;
@@ -609,7 +614,7 @@ static int launch(const uint8_t* actions, int8_t* out, int64_t n, int depth, cud
 	if (W3 > 0) {
 		const int64_t ctas = ((n + 31) / 32 + W3 - 1) / W3;
 		const int grid = (int)(ctas < RB_NUM_SMS ? ctas : RB_NUM_SMS);
-		size_t smem = (size_t)fixed_smem3(r2) + (size_t)W3 * 32 * depth;
+		size_t smem = (size_t)fixed_smem3(r2) + (size_t)W3 * 32 * depth + 16;
 		if (smem < (size_t)kMinSmem3) smem = kMinSmem3;
 		if (depth % 4 != 0) k_scramble_macro3<false, 1><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch);
 		else if (r2 == 1) k_scramble_macro3<true, 1><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch);

@@ -208,7 +208,7 @@ int rb_scramble(int rep, const uint8_t* actions, int64_t stride_cube, int64_t st
 			// output row), then one gather of the start state's sticker records through it
 			int rc = rbs::launch(actions, out, n, depth, S(stream), rb686::kStateBytes);
 			if (rc != RB_OK) return rc;
-			rb686::k_render_from2024<<<rb_grid(n, rb686::kWarps, 8), rb686::kThreads, 0, S(stream)>>>(out, start, n);
+			rb686::k_render_from2024<<<rb_grid((n + 31) / 32, rb686::kWarps, 8), rb686::kThreads, 0, S(stream)>>>(out, start, n);
 			RB_LAUNCHED("render_686");
 			return RB_OK;
 		}
