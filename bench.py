@@ -184,6 +184,10 @@ def run_gpu(args):
 	torch.cuda.set_device(local)
 	dev = torch.device("cuda", local)
 	if world > 1:
+		# stdout carries ONE JSON line: NCCL_DEBUG=VERSION makes NCCL printf its version to stdout, INFO / TRACE go to the debug file
+		if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+			os.environ["NCCL_DEBUG"] = "WARN"
+		os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 		dist.init_process_group("nccl", device_id=dev)
 	import rl_rubiks_b200  # noqa: F401  (raises if the CUDA library is missing: no CPU fallback)
 	from rl_rubiks_b200 import _native as N, adi, cube, sharding
