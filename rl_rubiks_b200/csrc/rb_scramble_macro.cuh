@@ -391,28 +391,25 @@ __device__ __forceinline__ uint32_t mod3_bytes(uint32_t c) {
 	return t ^ (x * 3u);
 }
 
-// Slot-major -> cubie-major int8[20], four slots per step in SIMD-within-register form; only the scatter by cubie id is
-// per byte.  `o` is this cube's 20-byte output row in shared memory.
-__device__ __forceinline__ void store_state_simd(uint8_t* __restrict__ o, const Slots& s) {
+// Inverse-element form (see k_scramble_macro3): byte q of the slot-major registers describes CUBIE q -- id field = its
+// position, twist accumulator = minus its twist, flip bits = its flip.  Per byte: corner value 3 * pos + ori with
+// ori = acc mod 3 where the position has negative chirality (0, 2, 5, 7: bit 0 == bit 2), its negation elsewhere;
+// edge value 2 * pos + flip.  The five words are the reference's int8[20] state.
+__device__ __forceinline__ void cubie_major(const Slots& s, uint32_t (&w)[5]) {
 #pragma unroll
 	for (int h = 0; h < 2; ++h) {
 		const uint32_t c = h ? s.C1 : s.C0;
-		const uint32_t neg = h ? 0xff00ff00u : 0x00ff00ffu;                      // positions 0, 2, 5, 7 carry the twist negated
 		const uint32_t t = mod3_bytes(c);
-		const uint32_t sw = ((t << 1) & 0x02020202u) | ((t >> 1) & 0x01010101u);   // 1 <-> 2
-		const uint32_t v = (h ? 0x15120f0cu : 0x09060300u) + ((t & ~neg) | (sw & neg));
-		const uint32_t id = (c >> 5) & 0x07070707u;
-#pragma unroll
-		for (int i = 0; i < 4; ++i) o[(id >> (8 * i)) & 0xffu] = (uint8_t)(v >> (8 * i));
+		const uint32_t sw = ((t << 1) & 0x02020202u) | ((t >> 1) & 0x01010101u);        // 1 <-> 2: minus t mod 3
+		const uint32_t p = (c >> 5) & 0x07070707u;
+		const uint32_t neg = (((p ^ (p >> 2)) & 0x01010101u) ^ 0x01010101u) * 255u;      // 0xff where bit 0 == bit 2
+		w[h] = p * 3u + ((t & neg) | (sw & ~neg));
 	}
 #pragma unroll
 	for (int d = 0; d < 3; ++d) {
 		const uint32_t e = d == 0 ? s.E0 : (d == 1 ? s.E1 : s.E2);
 		const uint32_t f = ((e >> 4) ^ (e >> 5) ^ (e >> 6)) & 0x01010101u;
-		const uint32_t v = (d == 0 ? 0x06040200u : (d == 1 ? 0x0e0c0a08u : 0x16141210u)) + f;
-		const uint32_t id = e & 0x0f0f0f0fu;
-#pragma unroll
-		for (int i = 0; i < 4; ++i) o[8u + ((id >> (8 * i)) & 0xffu)] = (uint8_t)(v >> (8 * i));
+		w[2 + d] = ((e & 0x0f0f0f0fu) << 1) + f;
 	}
 }
 
@@ -489,33 +486,44 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 				const uint32_t o1 = mad_u32(r, 16u * kRep1, off1), o2 = mad_u32(r, 4u * R2, off2);
 				apply_row(lds128(o1), lds32(o2), s);
 			};
-			// 12 moves = 3 action words = 4 rows; the row index a0 + 12 a1 + 144 a2 is one or two dp4a
+			// The kernel multiplies the INVERSE moves in REVERSE order: the slot-major product is then the inverse group element,
+			// whose byte q holds the position (and minus the twist) of CUBIE q -- the reference's cubie-major state up to a per-byte
+			// formula, so the result needs no scatter by cubie id (20 conflicting STS.U8 per cube otherwise).
+			// 12 moves = 3 action words = 4 rows, last move first; inverse action = a ^ 1, folded into the 4-bit mask; the row index
+			// b0 + 12 b1 + 144 b2 is one or two dp4a.
 			auto apply_words = [&](uint32_t w0, uint32_t w1, uint32_t w2) {
-				w0 &= 0x0f0f0f0fu; w1 &= 0x0f0f0f0fu; w2 &= 0x0f0f0f0fu;
-				apply3(__dp4a(w0, 0x00900C01u, 0u));
-				apply3(__dp4a(w0, 0x01000000u, __dp4a(w1, 0x0000900Cu, 0u)));
-				apply3(__dp4a(w1, 0x0C010000u, __dp4a(w2, 0x00000090u, 0u)));
-				apply3(__dp4a(w2, 0x900C0100u, 0u));
+				w0 = (w0 & 0x0f0f0f0fu) ^ 0x01010101u; w1 = (w1 & 0x0f0f0f0fu) ^ 0x01010101u; w2 = (w2 & 0x0f0f0f0fu) ^ 0x01010101u;
+				apply3(__dp4a(w2, 0x010C9000u, 0u));
+				apply3(__dp4a(w2, 0x00000001u, __dp4a(w1, 0x0C900000u, 0u)));
+				apply3(__dp4a(w1, 0x0000010Cu, __dp4a(w0, 0x90000000u, 0u)));
+				apply3(__dp4a(w0, 0x00010C90u, 0u));
 			};
-			int m = 0;
-			for (; m + 24 <= depth; m += 24) {                              // 8 rows add at most 16 to a twist accumulator <= 10
-				const uint32_t w0 = word_at(m), w1 = word_at(m + 4), w2 = word_at(m + 8), w3 = word_at(m + 12), w4 = word_at(m + 16),
-				               w5 = word_at(m + 20);
-				apply_words(w0, w1, w2); apply_words(w3, w4, w5);
-				s.C0 = fold_twists(s.C0); s.C1 = fold_twists(s.C1);
-			}
-			if (m < depth) {                                                // < 24 moves left: at most 4 + 3 + 1 rows
-				if (m + 12 <= depth) { apply_words(word_at(m), word_at(m + 4), word_at(m + 8)); m += 12; }
-				for (; m + 3 <= depth; m += 3) apply3((row[m] & 15u) + 12u * (row[m + 1] & 15u) + 144u * (row[m + 2] & 15u));
-				if (m < depth) {                                            // one or two trailing moves: 2-move row, identity padded
-					const uint32_t a0 = row[m] & 15u, a1 = m + 1 < depth ? row[m + 1] & 15u : 12u;
-					const uint8_t* r = tail + (a0 + 13u * a1) * 32u;
-					apply_row(*reinterpret_cast<const uint4*>(r), *reinterpret_cast<const uint32_t*>(r + 16), s);
+			auto inv_at = [&](int m) -> uint32_t { return (row[m] & 15u) ^ 1u; };
+			// the depth % 24 moves at the end of the sequence come first: at most 4 + 3 + 1 rows (8 byte-fetched rows when unaligned)
+			const int M = depth - depth % 24;
+			int pos = depth;
+			if (pos > M) {
+				if (kWordAligned && pos - 12 >= M) { apply_words(word_at(pos - 12), word_at(pos - 8), word_at(pos - 4)); pos -= 12; }
+				for (; pos - 3 >= M; pos -= 3) apply3(inv_at(pos - 1) + 12u * inv_at(pos - 2) + 144u * inv_at(pos - 3));
+				if (pos > M) {                                              // one or two moves left: 2-move row, identity padded
+					const uint32_t b0 = inv_at(pos - 1), b1 = pos - 2 >= M ? inv_at(pos - 2) : 12u;
+					const uint32_t r = smem_u32(tail) + (b0 + 13u * b1) * 32u;
+					apply_row(lds128(r), lds32(r + 16u), s);
 				}
 				s.C0 = fold_twists(s.C0); s.C1 = fold_twists(s.C1);
 			}
+			for (int m = M - 24; m >= 0; m -= 24) {                           // 8 rows add at most 16 to a twist accumulator <= 10
+				const uint32_t w0 = word_at(m), w1 = word_at(m + 4), w2 = word_at(m + 8), w3 = word_at(m + 12), w4 = word_at(m + 16),
+				               w5 = word_at(m + 20);
+				apply_words(w3, w4, w5); apply_words(w0, w1, w2);
+				s.C0 = fold_twists(s.C0); s.C1 = fold_twists(s.C1);
+			}
+			uint32_t res[5];
+			cubie_major(s, res);
 			__syncwarp(__activemask());                                   // every lane's action row is consumed: the buffer head is free
-			store_state_simd(buf + lane * 20, s);                         // results packed [cube][20] at the head of the warp's buffer
+			uint32_t* dst_row = reinterpret_cast<uint32_t*>(buf + lane * 20);   // results packed [cube][20] at the head of the warp's buffer
+#pragma unroll
+			for (int k = 0; k < 5; ++k) dst_row[k] = res[k];
 		}
 		__syncwarp();
 		{

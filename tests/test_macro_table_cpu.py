@@ -113,6 +113,62 @@ def test_macro3_scramble_emulation_matches_oracle(depth):
 	assert (_emulate(actions, rows, rows3, fold_every=8) == O.scramble_many(f, d, True)).all()
 
 
+def _emulate_inverse(actions, rows, rows3):
+	"""k_scramble_macro3 as shipped: the kernel multiplies the INVERSE moves in REVERSE order, so its slot-major result is the
+	inverse group element -- byte q then holds the position (and minus the twist) of CUBIE q, i.e. the reference's cubie-major
+	state up to a per-byte formula, with no scatter.  Row order as in the kernel: the depth % 24 remainder at the end of the
+	sequence first, then the 24-move groups from the last to the first; folds after the remainder and after every group."""
+	n, depth = actions.shape
+	inv = (actions.astype(np.int64) ^ 1)
+	C = np.tile((np.arange(8, dtype=np.uint8) << 5).astype(np.uint8), (n, 1))
+	E = np.tile(np.arange(12, dtype=np.uint8), (n, 1))
+
+	def apply(r, C, E):
+		sc, tf = r[:, 0], r[:, 4]
+		c0 = _prmt(C[:, :4], C[:, 4:], sc).astype(np.int64) + _bytes_of(tf & 0x03030303)
+		c1 = _prmt(C[:, :4], C[:, 4:], sc >> 16).astype(np.int64) + _bytes_of((tf >> 2) & 0x03030303)
+		assert (c0 < 256).all() and (c1 < 256).all() and ((c0 & 31) >= _bytes_of(tf & 0x03030303)).all()
+		C = np.concatenate([c0, c1], 1).astype(np.uint8)
+		Es = []
+		for d in range(3):
+			sel = r[:, 1 + d]
+			x = _prmt(E[:, :4], E[:, 4:8], sel)
+			Es.append(_prmt(x, E[:, 8:], sel >> 16) ^ _bytes_of(tf & (0x10101010 << d)))
+		return C, np.concatenate(Es, 1)
+
+	M = depth - depth % 24
+	pos = depth
+	while pos - 3 >= M:
+		C, E = apply(rows3[inv[:, pos - 1] + 12 * inv[:, pos - 2] + 144 * inv[:, pos - 3]], C, E)
+		pos -= 3
+	if pos > M:
+		a1 = inv[:, pos - 2] if pos - 2 >= M else np.full(n, 12, np.int64)
+		C, E = apply(rows[inv[:, pos - 1] + 13 * a1], C, E)
+	C = _fold(C)
+	for g in range(depth // 24 - 1, -1, -1):
+		for pos in range(24 * g + 24, 24 * g, -3):
+			C, E = apply(rows3[inv[:, pos - 1] + 12 * inv[:, pos - 2] + 144 * inv[:, pos - 3]], C, E)
+		C = _fold(C)
+	# per-byte conversion: cubie q sits at position id; its twist is minus the accumulated one
+	out = np.zeros((n, 20), dtype=np.int8)
+	p = (C >> 5).astype(np.int64)
+	t = (C & 31).astype(np.int64) % 3
+	neg = np.isin(p, (0, 2, 5, 7))
+	out[:, :8] = 3 * p + np.where(neg, t, (3 - t) % 3)
+	pe = (E & 15).astype(np.int64)
+	out[:, 8:] = 2 * pe + (((E >> 4) ^ (E >> 5) ^ (E >> 6)) & 1)
+	return out
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3, 4, 5, 11, 12, 13, 23, 24, 25, 26, 47, 48, 50, 99, 100, 101, 250])
+def test_macro3_inverse_sequence_emulation_matches_oracle(depth):
+	rows, rows3 = _table(), _table3()
+	g = np.random.RandomState(2000 + depth)
+	actions = g.randint(0, 12, (300, depth)).astype(np.uint8)
+	f, d = O.indices_to_actions(actions)
+	assert (_emulate_inverse(actions, rows, rows3) == O.scramble_many(f, d, True)).all()
+
+
 def test_macro_table_rows_are_permutations():
 	rows = _table()
 	sc = rows[:, 0]
