@@ -489,16 +489,24 @@ class AStarBatch:
 	Every search follows the reference's trace exactly (same pops, same state numbering, same G / parents / action queue).
 	20x24 representation."""
 
-	def __init__(self, net, lambda_: float, expansions: int):
+	def __init__(self, net, lambda_: float, expansions: int, oh_dtype=torch.float32):
 		N.require_cuda()
 		if not 0 < expansions <= 1024:
 			raise ValueError("expansions must be in 1..1024")
 		self.net, self.lambda_, self.expansions = net, float(lambda_), int(expansions)
+		# torch.bfloat16 (opt-in, not the reference's dtype): bf16 one-hot rows and a bf16-autocast forward of the value net
+		self.oh_dtype = oh_dtype
+		self._as_oh = cube._oh_fn("rb_as_oh", oh_dtype)
 		self.dev = torch.device("cuda", torch.cuda.current_device())
 
 	def _alloc(self, K: int, max_states: int):
 		dev, Nx = self.dev, self.expansions
 		M = max_states + 1
+		if getattr(self, "_shape", None) == (K, M, Nx):           # buffers of the previous search_many are reused (everything that
+			self.parents.zero_(); self.parent_actions.zero_()     # matters is re-initialised by rb_astar_init / rb_hashset_clear)
+			self.in_open.zero_()
+			return
+		self._shape = (K, M, Nx)
 		self.K, self.M = K, M
 		self.states = torch.empty(K, M, 20, dtype=torch.int8, device=dev)
 		self.G = torch.empty(K, M, dtype=torch.float64, device=dev)
@@ -519,7 +527,7 @@ class AStarBatch:
 		self.new_search = torch.empty(K * P, dtype=torch.int32, device=dev)
 		self.new_index = torch.empty(K * P, dtype=torch.int32, device=dev)
 		self.counters = torch.zeros(2, dtype=torch.int32, device=dev)          # n_new_total, n_active
-		self.oh = torch.empty(K * P, 480, dtype=torch.float32, device=dev)
+		self.oh = torch.empty(K * P, 480, dtype=self.oh_dtype, device=dev)
 		self.view = N.AStarView(K, M, Nx, *(N.ptr(t) for t in (self.states, self.G, self.parents, self.parent_actions, self.cost, self.in_open,
 																 self.count, self.n_sel, self.sel, self.won, self.solved_index, self.table)),
 								self.capacity, N.ptr(self.scratch))
@@ -555,8 +563,9 @@ class AStarBatch:
 		if n == 0:
 			return torch.zeros(1, dtype=torch.float32, device=self.dev)
 		oh = self.oh[:n]
-		N.check(N.lib.rb_as_oh(N.REP_2024, N.ptr(self.new_states), N.ptr(oh), n, N.stream_handle()))
-		val = self.net(oh, value=True, policy=False)
+		N.check(self._as_oh(N.REP_2024, N.ptr(self.new_states), N.ptr(oh), n, N.stream_handle()))
+		with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.oh_dtype == torch.bfloat16):
+			val = self.net(oh, value=True, policy=False)
 		return val.reshape(-1).float().contiguous()
 
 	def _results(self):

@@ -265,3 +265,6 @@ def test_astar_batch_matches_single_search_traces(golden, n_exp, max_states, lam
 			while i != 1:
 				q.insert(0, int(a.parent_actions[i])); i = int(a.parents[i])
 			assert q == queues[s]
+	# a second call on the same agent reuses every buffer and must reproduce the run
+	won2, queues2, count2 = agent.search_many(starts, max_states)
+	assert (won2 == won).all() and (count2 == count).all() and queues2 == queues

@@ -42,6 +42,7 @@ def main():
 	ap.add_argument("--lam", type=float, default=0.16)
 	ap.add_argument("--cheap-net", action="store_true")
 	ap.add_argument("--tf32", action="store_true")
+	ap.add_argument("--bf16", action="store_true", help="bf16 one-hot rows + bf16 autocast value forward (opt-in)")
 	args = ap.parse_args()
 	torch.manual_seed(0)
 	torch.backends.cuda.matmul.allow_tf32 = args.tf32
@@ -50,14 +51,15 @@ def main():
 	g = torch.Generator(device=dev); g.manual_seed(0)
 	acts = torch.randint(0, 12, (args.cubes, args.depth), dtype=torch.uint8, device=dev, generator=g)
 	starts = cube.scramble_batch(acts)
-	agent = frontier.AStarBatch(net, args.lam, args.expansions)
+	agent = frontier.AStarBatch(net, args.lam, args.expansions, oh_dtype=torch.bfloat16 if args.bf16 else torch.float32)
+	agent.search_many(starts, args.max_states, max_steps=1)           # warm-up: buffer allocation (~25 GB at 1000 cubes), cuBLAS heuristics
 	torch.cuda.synchronize()
 	t0 = time.perf_counter()
 	won, queues, count = agent.search_many(starts, args.max_states)
 	torch.cuda.synchronize()
 	dt = time.perf_counter() - t0
 	print(f"cubes {args.cubes} depth {args.depth} N {args.expansions} max_states {args.max_states} net {'cheap' if args.cheap_net else 'fc_small'}"
-		  f"{' tf32' if args.tf32 else ''}: steps {agent.steps} solved {int(won.sum())} states {int(count.sum())} in {dt:.3f} s = "
+		  f"{' tf32' if args.tf32 else ''}{' bf16' if args.bf16 else ''}: steps {agent.steps} solved {int(won.sum())} states {int(count.sum())} in {dt:.3f} s = "
 		  f"{count.sum() / dt / 1e6:.2f} M states/s ({count.sum() / max(agent.steps, 1) / args.cubes:.0f} new states/step/cube)")
 
 
