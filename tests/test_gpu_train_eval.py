@@ -123,3 +123,29 @@ def test_train_with_evaluator_hook_runs_and_tracks_best_net():
 	assert t.evaluation_rollouts.tolist() == [0, 1, 2] or t.evaluation_rollouts.tolist() == [0, 2]
 	assert len(t.sol_percents) == len(t.evaluation_rollouts) and all(0 <= p <= 1 for p in t.sol_percents)
 	assert np.isfinite(t.train_losses).all() and agent.net is trained
+
+
+def test_bf16_rows_keep_search_traces_and_train():
+	"""Opt-in bf16 one-hot rows: with the integer fake net every product and sum is exact in bf16 / f32 accumulation, so the
+	batched A* must reproduce the f32 run bit for bit; the training loop under bf16 autocast must track the f32 run closely."""
+	from rl_rubiks_b200.frontier import AStarBatch
+	from rl_rubiks_b200.train import Train
+	from oracle import cube_oracle as O
+	rng = np.random.RandomState(5)
+	w = rng.randint(-6, 7, 480).astype(np.float32)
+	starts = np.stack([O.scramble(rng.randint(0, 6, d), rng.randint(0, 2, d), True) for d in (1, 2, 3, 5, 8, 13)])
+	ref = AStarBatch(_FakeNet(w), lambda_=0.3, expansions=16).search_many(starts, 3000)
+	got = AStarBatch(_FakeNet(w), lambda_=0.3, expansions=16, oh_dtype=torch.bfloat16).search_many(starts, 3000)
+	assert (ref[0] == got[0]).all() and ref[1] == got[1] and (ref[2] == got[2]).all()
+
+	losses = {}
+	for dt in (torch.float32, torch.bfloat16):
+		torch.manual_seed(3)
+		net = _SmallNet().cuda()
+		t = Train(rollouts=3, batch_size=32, rollout_games=16, rollout_depth=6, optim_fn=torch.optim.Adam, alpha_update=0.5, lr=1e-3,
+				  gamma=1, update_interval=1, tau=1, reward_method="lapanfix", oh_dtype=dt)
+		np.random.seed(11)
+		t.train(net)
+		losses[dt] = t.train_losses.copy()
+	assert np.isfinite(losses[torch.bfloat16]).all()
+	np.testing.assert_allclose(losses[torch.bfloat16], losses[torch.float32], rtol=0.05)      # bf16 GEMMs: ~3 significant digits
