@@ -470,6 +470,7 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 		}
 		if (bulk) { mbar_wait(bar, parity); parity ^= 1u; }
 
+		uint32_t res[5] = {0u, 0u, 0u, 0u, 0u};
 		if ((int)lane < cnt) {
 			uint8_t* row = buf + lane * depth;
 			Slots s{0x60402000u, 0xe0c0a080u, 0x03020100u, 0x07060504u, 0x0b0a0908u};
@@ -518,9 +519,10 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 				apply_words(w3, w4, w5); apply_words(w0, w1, w2);
 				s.C0 = fold_twists(s.C0); s.C1 = fold_twists(s.C1);
 			}
-			uint32_t res[5];
 			cubie_major(s, res);
-			__syncwarp(__activemask());                                   // every lane's action row is consumed: the buffer head is free
+		}
+		__syncwarp();                                                     // every lane's action row is consumed: the buffer head is free
+		if ((int)lane < cnt) {
 			uint32_t* dst_row = reinterpret_cast<uint32_t*>(buf + lane * 20);   // results packed [cube][20] at the head of the warp's buffer
 #pragma unroll
 			for (int k = 0; k < 5; ++k) dst_row[k] = res[k];
