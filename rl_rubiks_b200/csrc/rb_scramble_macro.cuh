@@ -415,7 +415,10 @@ __device__ __forceinline__ void cubie_major(const Slots& s, uint32_t (&w)[5]) {
 
 template <bool kWordAligned, int R2>
 __global__ void __launch_bounds__(kMaxThreads, 1)
-k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out, int64_t n, int depth, int out_pitch) {
+k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out, int64_t n, int depth, int out_pitch,
+                  uint32_t p2_stride) {
+	// p2_stride = 4 * R2 arrives as a kernel argument so that the twist|flip word's address is an IMAD (FMA pipe) rather than
+	// the LEA (ALU pipe, the binding one) ptxas emits for a power-of-two constant
 	extern __shared__ __align__(128) uint8_t smem[];
 	constexpr int kP2Bytes3 = kP2Rows3 * 4 * R2;
 	uint8_t* table = smem;                                              // [P1 | P2 | tail | mbarriers | action buffers]
@@ -484,7 +487,7 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 				return __funnelshift_r(arow[m >> 2], arow[(m >> 2) + 1], ashift);
 			};
 			auto apply3 = [&](uint32_t r) {
-				const uint32_t o1 = mad_u32(r, 16u * kRep1, off1), o2 = mad_u32(r, 4u * R2, off2);
+				const uint32_t o1 = mad_u32(r, 16u * kRep1, off1), o2 = mad_u32(r, p2_stride, off2);
 				apply_row(lds128(o1), lds32(o2), s);
 			};
 			// The kernel multiplies the INVERSE moves in REVERSE order: the slot-major product is then the inverse group element,
@@ -626,10 +629,10 @@ static int launch(const uint8_t* actions, int8_t* out, int64_t n, int depth, cud
 		const int grid = (int)(ctas < RB_NUM_SMS ? ctas : RB_NUM_SMS);
 		size_t smem = (size_t)fixed_smem3(r2) + (size_t)W3 * 32 * depth + 16;
 		if (smem < (size_t)kMinSmem3) smem = kMinSmem3;
-		if (depth % 4 != 0) k_scramble_macro3<false, 1><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch);
-		else if (r2 == 1) k_scramble_macro3<true, 1><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch);
-		else if (r2 == 2) k_scramble_macro3<true, 2><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch);
-		else k_scramble_macro3<true, 4><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch);
+		if (depth % 4 != 0) k_scramble_macro3<false, 1><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch, 4u * 1);
+		else if (r2 == 1) k_scramble_macro3<true, 1><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch, 4u * 1);
+		else if (r2 == 2) k_scramble_macro3<true, 2><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch, 4u * 2);
+		else k_scramble_macro3<true, 4><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch, 4u * 4);
 		RB_LAUNCHED("scramble_macro3_2024");
 		return RB_OK;
 	}
