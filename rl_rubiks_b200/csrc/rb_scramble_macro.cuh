@@ -226,8 +226,12 @@ __device__ __forceinline__ void fill_table(uint8_t* table, const uint32_t* g_row
 // One base-4 digit fold of every twist accumulator (bits 0-4 of a corner byte): value mod 3 unchanged (4 == 1 mod 3),
 // any accumulator <= 31 becomes <= 3 + 7 = 10.  Between folds kReduceEvery rows add at most 2 each: 10 + 2 * 10 <= 31.
 __device__ __forceinline__ uint32_t fold_twists(uint32_t c) {
-	const uint32_t t = (c & 0x03030303u) + (shr_fma<2>(c) & 0x07070707u);
-	return (c & 0xe0e0e0e0u) | t;
+	// acc = 4 q + r  ->  q + r = acc - 3 q, per byte, without touching the id bits: one shift (IMAD.HI) and one multiply-add on
+	// the FMA pipe, one LOP3 on the ALU pipe (the masked form (c & 0xe0..) | ((c & 3..) + (c >> 2 & 7..)) costs three)
+	const uint32_t q = shr_fma<2>(c) & 0x07070707u;
+	uint32_t r;
+	asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(q), "r"(0xfffffffdu), "r"(c));
+	return r;
 }
 
 // Slot-major -> the reference's cubie-major int8[20] (written to this thread's 20-byte row in shared memory).
