@@ -43,7 +43,10 @@ constexpr int kSmemBudget = 227 * 1024;
 constexpr int kReduceEvery = 10;                // rows between twist folds (5 action words): 10 + 10 * 2 <= 31
 
 __device__ __align__(16) uint32_t g_macro[kRows * kRowWords + 3];
+// The 3-move kernel applies INVERSE moves (a ^ 1); its two device tables are stored pre-permuted -- entry (a0, a1, a2) holds the
+// row of (a0 ^ 1, a1 ^ 1, a2 ^ 1) -- so that the kernel indexes them with the raw action bytes (no XOR per action word).
 __device__ __align__(16) uint32_t g_macro3[12 * 12 * 12 * kRowWords + 3];
+__device__ __align__(16) uint32_t g_macro_tail_inv[13 * 13 * kRowWords + 3];
 
 struct Elem {                                   // one cube-group element in slot-major gather form
 	uint8_t csrc[8], ctw[8], esrc[12], efl[12];
@@ -115,6 +118,8 @@ constexpr int kRows3 = 12 * 12 * 12;            // 3-move rows, index a0 + 12 a1
 struct Host {
 	uint32_t rows[kRows * kRowWords + 3];
 	uint32_t rows3[kRows3 * kRowWords + 3];
+	uint32_t rows3_inv[kRows3 * kRowWords + 3];          // rows3 re-indexed by the inverse actions (device layout of g_macro3)
+	uint32_t rows_inv[kRows * kRowWords + 3];             // rows re-indexed likewise (identity 12 stays 12): g_macro_tail_inv
 	bool ok;
 };
 
@@ -139,6 +144,15 @@ static const Host& host() {
 						encode(y, h.rows3 + (a0 + 12 * a1 + 144 * a2) * kRowWords);
 					}
 			}
+		auto inv = [](int a) { return a < 12 ? a ^ 1 : a; };
+		for (int i = 0; i < kRows3; ++i) {
+			const int j = inv(i % 12) + 12 * inv(i / 12 % 12) + 144 * inv(i / 144);
+			memcpy(h.rows3_inv + i * kRowWords, h.rows3 + j * kRowWords, sizeof(uint32_t) * kRowWords);
+		}
+		for (int i = 0; i < kRows; ++i) {
+			const int j = inv(i % kA) + kA * inv(i / kA);
+			memcpy(h.rows_inv + i * kRowWords, h.rows + j * kRowWords, sizeof(uint32_t) * kRowWords);
+		}
 	});
 	return h;
 }
@@ -461,7 +475,7 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 		}
 	}
 	for (int i = threadIdx.x; i < kDevRows; i += blockDim.x) {
-		const uint32_t* r = g_macro + (i < kRows ? i : kRows - 1) * kRowWords;
+		const uint32_t* r = g_macro_tail_inv + (i < kRows ? i : kRows - 1) * kRowWords;
 		*reinterpret_cast<uint4*>(tail + i * 32) = make_uint4(r[0], r[1], r[2], r[3]);
 		*reinterpret_cast<uint32_t*>(tail + i * 32 + 16) = r[4];
 	}
@@ -497,16 +511,16 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 			// The kernel multiplies the INVERSE moves in REVERSE order: the slot-major product is then the inverse group element,
 			// whose byte q holds the position (and minus the twist) of CUBIE q -- the reference's cubie-major state up to a per-byte
 			// formula, so the result needs no scatter by cubie id (20 conflicting STS.U8 per cube otherwise).
-			// 12 moves = 3 action words = 4 rows, last move first; inverse action = a ^ 1, folded into the 4-bit mask; the row index
-			// b0 + 12 b1 + 144 b2 is one or two dp4a.
+			// 12 moves = 3 action words = 4 rows, last move first; the inversion a ^ 1 is folded into the tables' layout, the action
+			// bytes are only masked to 4 bits; the row index a0 + 12 a1 + 144 a2 (a0 = the later move) is one or two dp4a.
 			auto apply_words = [&](uint32_t w0, uint32_t w1, uint32_t w2) {
-				w0 = (w0 & 0x0f0f0f0fu) ^ 0x01010101u; w1 = (w1 & 0x0f0f0f0fu) ^ 0x01010101u; w2 = (w2 & 0x0f0f0f0fu) ^ 0x01010101u;
+				w0 &= 0x0f0f0f0fu; w1 &= 0x0f0f0f0fu; w2 &= 0x0f0f0f0fu;
 				apply3(__dp4a(w2, 0x010C9000u, 0u));
 				apply3(__dp4a(w2, 0x00000001u, __dp4a(w1, 0x0C900000u, 0u)));
 				apply3(__dp4a(w1, 0x0000010Cu, __dp4a(w0, 0x90000000u, 0u)));
 				apply3(__dp4a(w0, 0x00010C90u, 0u));
 			};
-			auto inv_at = [&](int m) -> uint32_t { return (row[m] & 15u) ^ 1u; };
+			auto inv_at = [&](int m) -> uint32_t { return row[m] & 15u; };     // raw action: the tables are indexed by it
 			// the depth % 24 moves at the end of the sequence come first: at most 4 + 3 + 1 rows (8 byte-fetched rows when unaligned)
 			const int M = depth - depth % 24;
 			int pos = depth;
@@ -587,7 +601,8 @@ static int ensure_device() {
 	const Host& h = host();
 	if (!h.ok) return rb_fail(RB_ERR_BAD_ARG, "macro-move table: corner twist is not additive for these move tables%s%s");
 	RB_CUDA(cudaMemcpyToSymbol(g_macro, h.rows, sizeof(h.rows)));
-	RB_CUDA(cudaMemcpyToSymbol(g_macro3, h.rows3, sizeof(h.rows3)));
+	RB_CUDA(cudaMemcpyToSymbol(g_macro3, h.rows3_inv, sizeof(h.rows3_inv)));
+	RB_CUDA(cudaMemcpyToSymbol(g_macro_tail_inv, h.rows_inv, sizeof(h.rows_inv)));
 	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro3<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
 	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro3<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
 	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro3<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
