@@ -549,31 +549,43 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 			for (int k = 0; k < 5; ++k) dst_row[k] = res[k];
 		}
 		__syncwarp();
+		// 32 cubes = 640 contiguous bytes in shared memory: each lane takes its five words into registers, the buffer is then
+		// free for the bulk copy of the warp's next chunk, which is started BEFORE the results leave for HBM (the stores, and
+		// their completion, are off the path that refills the buffer).  out_pitch = 20: also contiguous in HBM (288: parked at
+		// the head of a 6x8x6 row for the rb686 render).
+		uint32_t outw[5];
+#pragma unroll
+		for (int t = 0; t < 5; ++t) {
+			const int j = lane + 32 * t;
+			outw[t] = j < cnt * 5 ? reinterpret_cast<const uint32_t*>(buf)[j] : 0u;
+		}
+		// generic-proxy reads / writes of the buffer are ordered before the async-proxy refill
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		__syncwarp();
+		if (lane == 0 && chunk + stride < n_chunks) issue(chunk + stride);
 		{
-			// 32 cubes = 640 contiguous bytes in shared memory; out_pitch = 20: also contiguous in HBM (288: parked at the head of
-			// a 6x8x6 row for the rb686 render)
 			uint8_t* dst = reinterpret_cast<uint8_t*>(out) + chunk * 32 * out_pitch;
 			if (out_pitch == 20 && (reinterpret_cast<uintptr_t>(out) & 3u) == 0) {
 #pragma unroll
 				for (int t = 0; t < 5; ++t) {
 					const int j = lane + 32 * t;
-					if (j < cnt * 5) reinterpret_cast<uint32_t*>(dst)[j] = reinterpret_cast<const uint32_t*>(buf)[j];
+					if (j < cnt * 5) reinterpret_cast<uint32_t*>(dst)[j] = outw[t];
 				}
 			} else if ((reinterpret_cast<uintptr_t>(out) & 3u) == 0 && (out_pitch & 3) == 0) {
-				for (int i = lane; i < cnt * 5; i += 32) {
-					const int c = i / 5, k = i - 5 * c;
-					*reinterpret_cast<uint32_t*>(dst + c * out_pitch + 4 * k) = reinterpret_cast<const uint32_t*>(buf)[i];
+#pragma unroll
+				for (int t = 0; t < 5; ++t) {
+					const int j = lane + 32 * t, c = j / 5, k = j - 5 * c;
+					if (j < cnt * 5) *reinterpret_cast<uint32_t*>(dst + c * out_pitch + 4 * k) = outw[t];
 				}
 			} else {
-				for (int i = lane; i < cnt * 20; i += 32) {
-					const int c = i / 20, k = i - 20 * c;
-					dst[c * out_pitch + k] = buf[i];
+#pragma unroll
+				for (int t = 0; t < 5; ++t) {
+					const int j = lane + 32 * t, c = j / 5, k = j - 5 * c;
+					if (j < cnt * 5)
+						for (int q = 0; q < 4; ++q) dst[c * out_pitch + 4 * k + q] = (uint8_t)(outw[t] >> (8 * q));
 				}
 			}
 		}
-		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-		__syncwarp();
-		if (lane == 0 && chunk + stride < n_chunks) issue(chunk + stride);
 	}
 }
 
