@@ -525,12 +525,25 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 			const int M = depth - depth % 24;
 			int pos = depth;
 			if (pos > M) {
-				if (kWordAligned && pos - 12 >= M) { apply_words(word_at(pos - 12), word_at(pos - 8), word_at(pos - 4)); pos -= 12; }
-				for (; pos - 3 >= M; pos -= 3) apply3(inv_at(pos - 1) + 12u * inv_at(pos - 2) + 144u * inv_at(pos - 3));
-				if (pos > M) {                                              // one or two moves left: 2-move row, identity padded
-					const uint32_t b0 = inv_at(pos - 1), b1 = pos - 2 >= M ? inv_at(pos - 2) : 12u;
-					const uint32_t r = smem_u32(tail) + (b0 + 13u * b1) * 32u;
+				auto apply_tail = [&](uint32_t idx2) {                         // 2-move row (second move may be the identity, 12)
+					const uint32_t r = smem_u32(tail) + idx2 * 32u;
 					apply_row(lds128(r), lds32(r + 16u), s);
+				};
+				if (kWordAligned) {                                             // 4, 8, ..., 20 moves: whole words, indices by dp4a
+					if (pos - 12 >= M) { apply_words(word_at(pos - 12), word_at(pos - 8), word_at(pos - 4)); pos -= 12; }
+					if (pos - 8 >= M) {                                         // bytes 7..0: (7,6,5) (4,3,2) then the pair (1,0)
+						const uint32_t wa = word_at(pos - 8) & 0x0f0f0f0fu, wb = word_at(pos - 4) & 0x0f0f0f0fu;
+						apply3(__dp4a(wb, 0x010C9000u, 0u));
+						apply3(__dp4a(wb, 0x00000001u, __dp4a(wa, 0x0C900000u, 0u)));
+						apply_tail(__dp4a(wa, 0x0000010Du, 0u));
+					} else if (pos - 4 >= M) {                                  // bytes 3..0: (3,2,1) then the single move 0
+						const uint32_t wa = word_at(pos - 4) & 0x0f0f0f0fu;
+						apply3(__dp4a(wa, 0x010C9000u, 0u));
+						apply_tail((wa & 0xffu) + 13u * 12u);
+					}
+				} else {
+					for (; pos - 3 >= M; pos -= 3) apply3(inv_at(pos - 1) + 12u * inv_at(pos - 2) + 144u * inv_at(pos - 3));
+					if (pos > M) apply_tail(inv_at(pos - 1) + 13u * (pos - 2 >= M ? inv_at(pos - 2) : 12u));
 				}
 				s.C0 = fold_twists(s.C0); s.C1 = fold_twists(s.C1);
 			}
