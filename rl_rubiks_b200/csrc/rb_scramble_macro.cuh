@@ -409,6 +409,14 @@ __device__ __forceinline__ uint32_t mod3_bytes(uint32_t c) {
 	return t ^ (x * 3u);
 }
 
+// Same for accumulators that have just been folded (<= 10, fits 4 bits): two digit folds suffice.
+__device__ __forceinline__ uint32_t mod3_bytes_folded(uint32_t c) {
+	uint32_t t = (c & 0x03030303u) + ((c >> 2) & 0x03030303u);       // <= 3 + 2
+	t = (t & 0x03030303u) + ((t >> 2) & 0x01010101u);                 // 0..3, 3 == 0
+	const uint32_t x = t & (t >> 1) & 0x01010101u;
+	return t ^ (x * 3u);
+}
+
 // Inverse-element form (see k_scramble_macro3): byte q of the slot-major registers describes CUBIE q -- id field = its
 // position, twist accumulator = minus its twist, flip bits = its flip.  Per byte: corner value 3 * pos + ori with
 // ori = acc mod 3 where the position has negative chirality (0, 2, 5, 7: bit 0 == bit 2), its negation elsewhere;
@@ -417,7 +425,7 @@ __device__ __forceinline__ void cubie_major(const Slots& s, uint32_t (&w)[5]) {
 #pragma unroll
 	for (int h = 0; h < 2; ++h) {
 		const uint32_t c = h ? s.C1 : s.C0;
-		const uint32_t t = mod3_bytes(c);
+		const uint32_t t = mod3_bytes_folded(c);
 		const uint32_t sw = ((t << 1) & 0x02020202u) | ((t >> 1) & 0x01010101u);        // 1 <-> 2: minus t mod 3
 		const uint32_t p = (c >> 5) & 0x07070707u;
 		const uint32_t neg = (((p ^ (p >> 2)) & 0x01010101u) ^ 0x01010101u) * 255u;      // 0xff where bit 0 == bit 2
@@ -547,12 +555,15 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 				}
 				s.C0 = fold_twists(s.C0); s.C1 = fold_twists(s.C1);
 			}
-			for (int m = M - 24; m >= 0; m -= 24) {                           // 8 rows add at most 16 to a twist accumulator <= 10
+			auto group24 = [&](int m) {                                       // 8 rows add at most 16 to a twist accumulator <= 10
 				const uint32_t w0 = word_at(m), w1 = word_at(m + 4), w2 = word_at(m + 8), w3 = word_at(m + 12), w4 = word_at(m + 16),
 				               w5 = word_at(m + 20);
 				apply_words(w3, w4, w5); apply_words(w0, w1, w2);
 				s.C0 = fold_twists(s.C0); s.C1 = fold_twists(s.C1);
-			}
+			};
+			int m = M - 24;
+			for (; m >= 24; m -= 48) { group24(m); group24(m - 24); }          // two groups per trip: half the loop bookkeeping
+			if (m >= 0) group24(m);
 			cubie_major(s, res);
 		}
 		__syncwarp();                                                     // every lane's action row is consumed: the buffer head is free
