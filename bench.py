@@ -29,8 +29,8 @@ N_CUBES = 1 << 24
 DEPTH = 100
 BYTES_PER_CUBE = DEPTH + 20          # uint8 actions in + int8[20] state out
 # dram__bytes_read.sum + dram__bytes_write.sum of one 2^24-cube launch, from the ncu --set full capture summarised in
-# profiles/r1p_scramble_macro3_ncu.txt (1.677787 GB + 0.324196 GB): the kernel moves exactly its algorithmic bytes.
-NCU_DRAM_BYTES_PER_CUBE = (1.677787e9 + 0.324196e9) / (1 << 24)
+# profiles/r1q_scramble_macro3_ncu.txt (1.677844 GB + 0.322344 GB): the kernel moves exactly its algorithmic bytes.
+NCU_DRAM_BYTES_PER_CUBE = (1.677844e9 + 0.322344e9) / (1 << 24)
 METRIC, UNIT = "cube_moves_per_sec", "moves/s"
 WORKLOAD = "raw scramble: 2^24 cubes x 100 random moves per GPU, 20x24 rep, packed int8 (BASELINE configs[1])"
 
@@ -292,10 +292,10 @@ def run_gpu(args):
 		"config": {"workload": WORKLOAD, "cubes_per_gpu": n, "depth": depth, "actions": "host-supplied uint8 [n][100], resident in HBM",
 				   "l2": "inputs (1.68 GB actions) larger than the 126 MB L2, no reuse between steps", "parity_subsample_ok": parity_ok},
 		"roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": int(NCU_DRAM_BYTES_PER_CUBE * n),
-					 "traffic_source": "ncu --set full, profiles/r1p_scramble_macro3_ncu.txt (dram read + write per launch, scaled by cubes)",
+					 "traffic_source": "ncu --set full, profiles/r1q_scramble_macro3_ncu.txt (dram read + write per launch, scaled by cubes)",
 					 "peak_source": peak_src, "kernel": "rbs::k_scramble_macro3<true, 1>", "kernel_ms": kernel_ms,
 					 "algorithmic_bytes_per_launch": BYTES_PER_CUBE * n,
-					 "note": "multi-move scramble is bound by shared-memory table wavefronts (l1tex 91 %) and the integer ALU pipe (70 %), not HBM: see DESIGN.md 3.1"},
+					 "note": "multi-move scramble is bound by shared-memory table wavefronts (l1tex 94 %) and the integer ALU pipe (66 %), not HBM: see DESIGN.md 3.1"},
 		"cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
 						 "sample": f"{cores} processes x {cpu_chunks * CPU_CHUNK} cubes x {depth} moves, numpy oracle port, {cpu_dt:.1f} s"},
 		"e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * depth, "d2h_bytes_per_step": n * 20,
