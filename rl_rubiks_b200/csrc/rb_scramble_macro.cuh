@@ -439,12 +439,16 @@ __device__ __forceinline__ void cubie_major(const Slots& s, uint32_t (&w)[5]) {
 	}
 }
 
-template <bool kWordAligned, int R2>
+// kMode: 0 = any depth (unaligned rows, funnel-shifted words), 1 = depth % 4 == 0 (word loads), 2 = depth % 16 == 0 (16-byte
+// loads in the main loop), 3 = depth % 128 == 0 (16-byte loads from padded rows).  Separate instantiations keep the common
+// mode-1 kernel (depth 100) free of the other modes' code.
+template <int kMode, int R2>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out, int64_t n, int depth, int out_pitch,
                   uint32_t p2_stride) {
 	// p2_stride = 4 * R2 arrives as a kernel argument so that the twist|flip word's address is an IMAD (FMA pipe) rather than
 	// the LEA (ALU pipe, the binding one) ptxas emits for a power-of-two constant
+	constexpr bool kWordAligned = kMode >= 1;
 	extern __shared__ __align__(128) uint8_t smem[];
 	constexpr int kP2Bytes3 = kP2Rows3 * 4 * R2;
 	uint8_t* table = smem;                                              // [P1 | P2 | tail | mbarriers | action buffers]
@@ -452,7 +456,14 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 	uint64_t* bars = reinterpret_cast<uint64_t*>(tail + kTailBytes);
 	const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
 	const int chunk_bytes = 32 * depth;
-	uint8_t* buf = reinterpret_cast<uint8_t*>(bars) + kMaxThreads / 32 * 8 + (size_t)wib * chunk_bytes;
+	// depth % 16 == 0: the main loop reads the action rows with 16-byte loads (a16).  depth % 128 == 0: the rows are 128 bytes
+	// apart or a multiple, every lane in the same bank group (8-way conflicts even for 16-byte loads, 32-way for words); those
+	// chunks are copied row by row (32 bulk copies, one per lane -- dearer than one 3200-byte copy, worth it only here) into
+	// rows of pitch depth + 16, whose 16-byte stride is odd: conflict free.  Measured, 2^24 cubes: depth 64 1.00 -> 0.76 ms,
+	// 96 1.08 -> 0.82 ms (16-byte loads), 128 2.91 -> 1.33 ms (padded rows).
+	constexpr bool a16 = kMode >= 2, pad16 = kMode == 3;
+	const int pitch = depth + (pad16 ? 16 : 0);
+	uint8_t* buf = reinterpret_cast<uint8_t*>(bars) + kMaxThreads / 32 * 8 + (size_t)wib * (32 * pitch);
 	uint64_t* bar = &bars[wib];
 	const uint32_t off1 = smem_u32(table) + (lane & (kRep1 - 1)) * 16u, off2 = smem_u32(table) + (uint32_t)kP1Bytes3 + (lane & (R2 - 1)) * 4u;
 
@@ -460,18 +471,25 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 	const int64_t stride = (int64_t)gridDim.x * n_warps;
 	int64_t chunk = (int64_t)blockIdx.x * n_warps + wib;
 
-	auto issue = [&](int64_t c) {
+	auto issue = [&](int64_t c) {                             // warp-wide: starts the bulk copy (copies) of chunk c into this warp's buffer
+		if (c >= n_chunks) return;
 		const int cnt = (int)min((int64_t)32, n - c * 32);
-		const uint32_t bulk = (uint32_t)(cnt * depth) & ~15u;
-		if (bulk) {
-			mbar_expect_tx(bar, bulk);
-			bulk_g2s(buf, actions + c * chunk_bytes, bulk, bar);
+		if (pad16) {
+			if (lane == 0) mbar_expect_tx(bar, (uint32_t)(cnt * depth));
+			__syncwarp();
+			if ((int)lane < cnt) bulk_g2s(buf + lane * pitch, actions + c * chunk_bytes + (int64_t)lane * depth, (uint32_t)depth, bar);
+		} else if (lane == 0) {
+			const uint32_t bulk = (uint32_t)(cnt * depth) & ~15u;
+			if (bulk) {
+				mbar_expect_tx(bar, bulk);
+				bulk_g2s(buf, actions + c * chunk_bytes, bulk, bar);
+			}
 		}
 	};
 	if (lane == 0) mbar_init(bar, 1);
 	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	__syncwarp();
-	if (lane == 0 && chunk < n_chunks) issue(chunk);
+	issue(chunk);
 	for (int i = threadIdx.x; i < kP2Rows3 * kRep1; i += blockDim.x) {
 		const int row = i / kRep1, c = i % kRep1;
 		if (row < kRows3) {
@@ -501,7 +519,7 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 
 		uint32_t res[5] = {0u, 0u, 0u, 0u, 0u};
 		if ((int)lane < cnt) {
-			uint8_t* row = buf + lane * depth;
+			uint8_t* row = buf + lane * pitch;
 			Slots s{0x60402000u, 0xe0c0a080u, 0x03020100u, 0x07060504u, 0x0b0a0908u};
 			// depth % 4 != 0: rows start at any byte; two aligned words and one funnel shift give the four action bytes at m
 			// (m is a multiple of 4 here; the word after the row's last one may belong to the next row or to the 16 bytes of
@@ -561,9 +579,24 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 				apply_words(w3, w4, w5); apply_words(w0, w1, w2);
 				s.C0 = fold_twists(s.C0); s.C1 = fold_twists(s.C1);
 			};
+			// Two groups (48 moves) per trip, anchored at multiples of 48 from the row start: half the loop bookkeeping, and for
+			// depth % 16 == 0 the 12 action words are three 16-byte loads -- rows whose word stride is a multiple of 8 (depth 32, 64,
+			// 96, ...) would read single words with 8- to 16-way bank conflicts, 16-byte loads cut that four-fold.
 			int m = M - 24;
-			for (; m >= 24; m -= 48) { group24(m); group24(m - 24); }          // two groups per trip: half the loop bookkeeping
-			if (m >= 0) group24(m);
+			if (a16 && ((M / 24) & 1)) { group24(m); m -= 24; }
+			if (a16) {
+				for (; m >= 24; m -= 48) {
+					const uint4* q = reinterpret_cast<const uint4*>(row + (m - 24));
+					const uint4 q0 = q[0], q1 = q[1], q2 = q[2];
+					apply_words(q2.y, q2.z, q2.w); apply_words(q1.z, q1.w, q2.x);
+					s.C0 = fold_twists(s.C0); s.C1 = fold_twists(s.C1);
+					apply_words(q0.w, q1.x, q1.y); apply_words(q0.x, q0.y, q0.z);
+					s.C0 = fold_twists(s.C0); s.C1 = fold_twists(s.C1);
+				}
+			} else {
+				for (; m >= 24; m -= 48) { group24(m); group24(m - 24); }
+				if (m >= 0) group24(m);
+			}
 			cubie_major(s, res);
 		}
 		__syncwarp();                                                     // every lane's action row is consumed: the buffer head is free
@@ -586,7 +619,7 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 		// generic-proxy reads / writes of the buffer are ordered before the async-proxy refill
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 		__syncwarp();
-		if (lane == 0 && chunk + stride < n_chunks) issue(chunk + stride);
+		issue(chunk + stride);
 		{
 			uint8_t* dst = reinterpret_cast<uint8_t*>(out) + chunk * 32 * out_pitch;
 			if (out_pitch == 20 && (reinterpret_cast<uintptr_t>(out) & 3u) == 0) {
@@ -639,10 +672,12 @@ static int ensure_device() {
 	RB_CUDA(cudaMemcpyToSymbol(g_macro, h.rows, sizeof(h.rows)));
 	RB_CUDA(cudaMemcpyToSymbol(g_macro3, h.rows3_inv, sizeof(h.rows3_inv)));
 	RB_CUDA(cudaMemcpyToSymbol(g_macro_tail_inv, h.rows_inv, sizeof(h.rows_inv)));
-	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro3<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro3<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro3<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro3<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro3<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro3<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro3<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro3<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro3<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro3<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
 	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
 	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
 	done[dev] = true;
@@ -663,9 +698,10 @@ static int warps_for(int64_t n, int depth) {
 
 // 3-move kernel: fixed shared memory and warps per CTA for a given depth (0: use the 2-move kernel)
 static int64_t fixed_smem3(int r2) { return (int64_t)kP1Bytes3 + (int64_t)kP2Rows3 * 4 * r2 + kTailBytes + kMaxThreads / 32 * 8; }
+static int pitch3(int depth) { return depth % 128 == 0 ? depth + 16 : depth; }     // row pitch of the action buffers (see the kernel)
 static int warps_for3(int64_t n, int depth, int r2) {
 	if (depth < 20) return 0;
-	int64_t w = (kSmemBudget - 16 - fixed_smem3(r2)) / (32 * (int64_t)depth);
+	int64_t w = (kSmemBudget - 16 - fixed_smem3(r2)) / (32 * (int64_t)pitch3(depth));
 	if (w > max_threads() / 32) w = max_threads() / 32;
 	if (w < 8) return 0;                         // long sequences: too few resident warps to hide the table latency
 	const int64_t spread = ((n + 31) / 32 + RB_NUM_SMS - 1) / RB_NUM_SMS;
@@ -677,17 +713,19 @@ static int launch(const uint8_t* actions, int8_t* out, int64_t n, int depth, cud
 	int rc = ensure_device();
 	if (rc != RB_OK) return rc;
 	static const int rows_per = env_int("RB_SCRAMBLE_MOVES_PER_ROW", 3), r2_env = env_int("RB_SCRAMBLE_R2", 1);
-	const int r2 = (depth % 4 == 0 && (r2_env == 2 || r2_env == 4)) ? r2_env : 1;
+	const int r2 = (depth % 4 == 0 && depth % 16 != 0 && (r2_env == 2 || r2_env == 4)) ? r2_env : 1;
 	const int W3 = rows_per == 3 ? warps_for3(n, depth, r2) : 0;
 	if (W3 > 0) {
 		const int64_t ctas = ((n + 31) / 32 + W3 - 1) / W3;
 		const int grid = (int)(ctas < RB_NUM_SMS ? ctas : RB_NUM_SMS);
-		size_t smem = (size_t)fixed_smem3(r2) + (size_t)W3 * 32 * depth + 16;
+		size_t smem = (size_t)fixed_smem3(r2) + (size_t)W3 * 32 * pitch3(depth) + 16;
 		if (smem < (size_t)kMinSmem3) smem = kMinSmem3;
-		if (depth % 4 != 0) k_scramble_macro3<false, 1><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch, 4u * 1);
-		else if (r2 == 1) k_scramble_macro3<true, 1><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch, 4u * 1);
-		else if (r2 == 2) k_scramble_macro3<true, 2><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch, 4u * 2);
-		else k_scramble_macro3<true, 4><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch, 4u * 4);
+		if (depth % 4 != 0) k_scramble_macro3<0, 1><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch, 4u);
+		else if (depth % 128 == 0) k_scramble_macro3<3, 1><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch, 4u);
+		else if (depth % 16 == 0) k_scramble_macro3<2, 1><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch, 4u);
+		else if (r2 == 2) k_scramble_macro3<1, 2><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch, 8u);
+		else if (r2 == 4) k_scramble_macro3<1, 4><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch, 16u);
+		else k_scramble_macro3<1, 1><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch, 4u);
 		RB_LAUNCHED("scramble_macro3_2024");
 		return RB_OK;
 	}
