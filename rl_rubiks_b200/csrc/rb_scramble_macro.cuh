@@ -1,29 +1,28 @@
 // Fast multi-move scramble for the 20x24 representation (BASELINE configs[1]: 2^24 cubes x 100 moves).
 //
 // The byte-LUT kernel (rb2024::k_scramble) does 20 data-dependent shared-memory lookups per move and is bound by
-// shared-memory bank conflicts at ~2 % of the HBM roofline (profiles/r1a_scramble_v1_ncu.txt).  This kernel changes the
+// shared-memory bank conflicts at ~2 % of the HBM roofline (profiles/r1a_scramble_v1_ncu.txt).  The kernels here change the
 // representation instead of the table: inside the kernel a cube is kept "slot-major" -- which cubie sits in each of
 // the 8 corner / 12 edge positions -- so that a move is a FIXED byte permutation of registers (PRMT with a selector
 // that depends only on the action) plus an additive orientation update:
 //   corners: 8 bytes (C0,C1), byte = twist accumulator (bits 0-4, value mod 3 is the twist) | cubie id << 5
 //   edges  : 12 bytes (E0,E1,E2), byte = cubie id (bits 0-3) | three partial flip bits (4-6) whose parity is the flip
-// Permutation + additive orientation is closed under composition, so two consecutive moves are fused into one table
-// row (13^2 rows, index a0 + 13 a1, action 12 = identity padding) of five words: corner selectors, three edge selector
-// words and one word carrying the 8 twist increments and 12 flip bits.  Per 2 moves a thread does LDS.128 + LDS.32,
-// 8 PRMT and ~7 other ALU-pipe instructions (shifts and adds go to the FMA pipe as IMAD) instead of 40 LDS.U8 and
-// ~120 ALU instructions.  The table is replicated in shared memory so that lane l always reads bank group l % 8
-// (16-byte part) resp. bank l (4-byte part): every fetch of 32 random rows is bank-conflict free (54 KB).
-// A 3-move table (13^3 rows) needs fewer rows per cube but cannot be replicated (281 KB); its random fetches cost
-// 2.7x the conflict-free wavefronts and pinned the kernel on the shared-memory crossbar (profiles/r1c_*).
-// The reference's cubie-major int8[20] state is rebuilt once per cube at the end (scatter through shared memory).
+// Permutation + additive orientation is closed under composition, so k consecutive moves are fused into one table row of
+// five words: corner selectors, three edge selector words and one word carrying the 8 twist increments and 12 flip bits.
+//
+//   k_scramble_macro3 (the one that runs for depth <= 400): rows of THREE moves (12^3), four copies of the 16-byte part,
+//     the product taken backwards (inverse moves, reverse order) so that the registers end up cubie-major -- see the
+//     comments at the kernel.  0.83 ms for 2^24 x 100 moves, at the shared-memory bound of this table design.
+//   k_scramble_macro (fallback for longer sequences): rows of TWO moves (13^2 with identity padding), the table replicated
+//     so that every fetch is bank-conflict free (64 KB), forward product, scatter to cubie-major at the end.
 //
 // The corner twist t relates to the reference's orientation o (the axis the tracked sticker faces, maps.py:128)
 // by t = o for positions {1,3,4,6} and t = -o mod 3 for positions {0,2,5,7} (the corner's chirality, the same split
 // cube.py:292 uses); with that labelling every quarter turn adds a constant per slot.  rbs::host() derives all
 // rows from the 20x24 LUT and verifies the additivity for every (action, position, orientation).
 //
-// Action tiles ([T cubes][depth] bytes, contiguous in HBM) are brought into shared memory with one 1-D bulk
-// async copy (cp.async.bulk, TMA engine, completion on an mbarrier), double buffered against the compute.
+// Action tiles ([32 cubes][depth] bytes per warp, contiguous in HBM) are brought into shared memory with 1-D bulk
+// async copies (cp.async.bulk, TMA engine, completion on the warp's mbarrier).
 #pragma once
 #include "rb_common.cuh"
 #include "rb_tables.cuh"
@@ -400,16 +399,8 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a) {
 	return v;
 }
 
-// Per byte: 5-bit twist accumulator (bits 0-4) -> its value mod 3, by base-4 digit folds (4 == 1 mod 3); other bits ignored.
-__device__ __forceinline__ uint32_t mod3_bytes(uint32_t c) {
-	uint32_t t = (c & 0x03030303u) + ((c >> 2) & 0x07070707u);       // <= 3 + 7
-	t = (t & 0x03030303u) + ((t >> 2) & 0x03030303u);                 // <= 3 + 2
-	t = (t & 0x03030303u) + ((t >> 2) & 0x01010101u);                 // 0..3, 3 == 0
-	const uint32_t x = t & (t >> 1) & 0x01010101u;
-	return t ^ (x * 3u);
-}
-
-// Same for accumulators that have just been folded (<= 10, fits 4 bits): two digit folds suffice.
+// Per byte: twist accumulator (bits 0-4) -> its value mod 3, by base-4 digit folds (4 == 1 mod 3); other bits ignored.
+// The accumulators have just been folded (<= 10, fits 4 bits): two digit folds suffice.
 __device__ __forceinline__ uint32_t mod3_bytes_folded(uint32_t c) {
 	uint32_t t = (c & 0x03030303u) + ((c >> 2) & 0x03030303u);       // <= 3 + 2
 	t = (t & 0x03030303u) + ((t >> 2) & 0x01010101u);                 // 0..3, 3 == 0
