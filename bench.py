@@ -309,7 +309,9 @@ def run_gpu(args):
 					 "traffic_source": "ncu --set full, profiles/r1q_scramble_macro3_ncu.txt (dram read + write per launch, scaled by cubes)",
 					 "peak_source": peak_src, "kernel": "rbs::k_scramble_macro3<true, 1>", "kernel_ms": kernel_ms,
 					 "algorithmic_bytes_per_launch": BYTES_PER_CUBE * n,
-					 "note": "multi-move scramble is bound by shared-memory table wavefronts (l1tex 94 %) and the integer ALU pipe (66 %), not HBM: see DESIGN.md 3.1"},
+					 "note": "multi-move scramble is bound by shared-memory table wavefronts (l1tex 94 %) and the integer ALU pipe (66 %), not HBM: see DESIGN.md 3.1",
+					 "limiter": {"resource": "shared-memory wavefronts (l1tex)", "pct_of_peak": 94.2, "alu_pipe_pct": 65.8, "dram_pct": 28.7,
+								 "source": "ncu --set full, profiles/r1q_scramble_macro3_ncu.txt"}},
 		"cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
 						 "sample": f"{cores} processes x {cpu_chunks * CPU_CHUNK} cubes x {depth} moves, numpy oracle port, {cpu_dt:.1f} s"},
 		"e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * depth, "d2h_bytes_per_step": n * 20,
