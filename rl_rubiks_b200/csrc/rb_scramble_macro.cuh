@@ -540,51 +540,70 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 			auto inv_at = [&](int m) -> uint32_t { return row[m] & 15u; };     // raw action: the tables are indexed by it
 			// the depth % 24 moves at the end of the sequence come first: at most 4 + 3 + 1 rows (8 byte-fetched rows when unaligned)
 			const int M = depth - depth % 24;
-			int pos = depth;
-			if (pos > M) {
-				auto apply_tail = [&](uint32_t idx2) {                         // 2-move row (second move may be the identity, 12)
-					const uint32_t r = smem_u32(tail) + idx2 * 32u;
-					apply_row(lds128(r), lds32(r + 16u), s);
-				};
-				if (kWordAligned) {                                             // 4, 8, ..., 20 moves: whole words, indices by dp4a
-					if (pos - 12 >= M) { apply_words(word_at(pos - 12), word_at(pos - 8), word_at(pos - 4)); pos -= 12; }
-					if (pos - 8 >= M) {                                         // bytes 7..0: (7,6,5) (4,3,2) then the pair (1,0)
-						const uint32_t wa = word_at(pos - 8) & 0x0f0f0f0fu, wb = word_at(pos - 4) & 0x0f0f0f0fu;
-						apply3(__dp4a(wb, 0x010C9000u, 0u));
-						apply3(__dp4a(wb, 0x00000001u, __dp4a(wa, 0x0C900000u, 0u)));
-						apply_tail(__dp4a(wa, 0x0000010Du, 0u));
-					} else if (pos - 4 >= M) {                                  // bytes 3..0: (3,2,1) then the single move 0
-						const uint32_t wa = word_at(pos - 4) & 0x0f0f0f0fu;
-						apply3(__dp4a(wa, 0x010C9000u, 0u));
-						apply_tail((wa & 0xffu) + 13u * 12u);
-					}
-				} else {
-					for (; pos - 3 >= M; pos -= 3) apply3(inv_at(pos - 1) + 12u * inv_at(pos - 2) + 144u * inv_at(pos - 3));
-					if (pos > M) apply_tail(inv_at(pos - 1) + 13u * (pos - 2 >= M ? inv_at(pos - 2) : 12u));
-				}
-				s.C0 = fold_twists(s.C0); s.C1 = fold_twists(s.C1);
-			}
-			auto group24 = [&](int m) {                                       // 8 rows add at most 16 to a twist accumulator <= 10
-				const uint32_t w0 = word_at(m), w1 = word_at(m + 4), w2 = word_at(m + 8), w3 = word_at(m + 12), w4 = word_at(m + 16),
-				               w5 = word_at(m + 20);
-				apply_words(w3, w4, w5); apply_words(w0, w1, w2);
-				s.C0 = fold_twists(s.C0); s.C1 = fold_twists(s.C1);
+			auto apply_tail = [&](uint32_t idx2) {                             // 2-move row (second move may be the identity, 12)
+				const uint32_t r = smem_u32(tail) + idx2 * 32u;
+				apply_row(lds128(r), lds32(r + 16u), s);
 			};
-			// Two groups (48 moves) per trip, anchored at multiples of 48 from the row start: half the loop bookkeeping, and for
-			// depth % 16 == 0 the 12 action words are three 16-byte loads -- rows whose word stride is a multiple of 8 (depth 32, 64,
-			// 96, ...) would read single words with 8- to 16-way bank conflicts, 16-byte loads cut that four-fold.
+			auto rem8 = [&](uint32_t wa, uint32_t wb) {                        // 8 moves, bytes 7..0: (7,6,5) (4,3,2) then the pair (1,0)
+				wa &= 0x0f0f0f0fu; wb &= 0x0f0f0f0fu;
+				apply3(__dp4a(wb, 0x010C9000u, 0u));
+				apply3(__dp4a(wb, 0x00000001u, __dp4a(wa, 0x0C900000u, 0u)));
+				apply_tail(__dp4a(wa, 0x0000010Du, 0u));
+			};
+			auto rem4 = [&](uint32_t wa) {                                     // 4 moves, bytes 3..0: (3,2,1) then the single move 0
+				wa &= 0x0f0f0f0fu;
+				apply3(__dp4a(wa, 0x010C9000u, 0u));
+				apply_tail((wa & 0xffu) + 13u * 12u);
+			};
+			auto fold = [&]() { s.C0 = fold_twists(s.C0); s.C1 = fold_twists(s.C1); };
+			auto group24w = [&](uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, uint32_t w5) {
+				apply_words(w3, w4, w5); apply_words(w0, w1, w2);              // 8 rows add at most 16 to a twist accumulator <= 10
+				fold();
+			};
+			auto group24 = [&](int m) { group24w(word_at(m), word_at(m + 4), word_at(m + 8), word_at(m + 12), word_at(m + 16), word_at(m + 20)); };
 			int m = M - 24;
-			if (a16 && ((M / 24) & 1)) { group24(m); m -= 24; }
 			if (a16) {
+				// depth % 16 == 0 (so depth % 24 is 0, 8 or 16): rows whose word stride is a multiple of 8 (depth 32, 64, 96, ...) would
+				// read single words with 8- to 32-way bank conflicts, 16-byte loads cut that four-fold.  Pairs of groups are anchored at
+				// multiples of 48 from the row start; what lies above them -- an odd group and / or the remainder -- is at most 40 bytes
+				// starting 16-byte aligned and is taken with two or three 16-byte loads as well (the last may run 8 bytes past the row).
+				const int rem = depth - M, top = (M / 48) * 48;
+				const bool odd = (M / 24) & 1;
+				const uint4* q = reinterpret_cast<const uint4*>(row + top);
+				if (odd) {
+					const uint4 q0 = q[0], q1 = q[1];
+					if (rem == 8) { rem8(q1.z, q1.w); fold(); }
+					else if (rem == 16) { const uint4 q2 = q[2]; apply_words(q1.w, q2.x, q2.y); rem4(q1.z); fold(); }
+					group24w(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y);
+					m -= 24;
+				} else if (rem) {
+					const uint4 q0 = q[0];
+					if (rem == 8) rem8(q0.x, q0.y);
+					else { apply_words(q0.y, q0.z, q0.w); rem4(q0.x); }
+					fold();
+				}
 				for (; m >= 24; m -= 48) {
-					const uint4* q = reinterpret_cast<const uint4*>(row + (m - 24));
-					const uint4 q0 = q[0], q1 = q[1], q2 = q[2];
+					const uint4* p = reinterpret_cast<const uint4*>(row + (m - 24));
+					const uint4 q0 = p[0], q1 = p[1], q2 = p[2];
 					apply_words(q2.y, q2.z, q2.w); apply_words(q1.z, q1.w, q2.x);
-					s.C0 = fold_twists(s.C0); s.C1 = fold_twists(s.C1);
+					fold();
 					apply_words(q0.w, q1.x, q1.y); apply_words(q0.x, q0.y, q0.z);
-					s.C0 = fold_twists(s.C0); s.C1 = fold_twists(s.C1);
+					fold();
 				}
 			} else {
+				int pos = depth;
+				if (pos > M) {
+					if (kWordAligned) {                                         // 4, 8, ..., 20 moves: whole words, indices by dp4a
+						if (pos - 12 >= M) { apply_words(word_at(pos - 12), word_at(pos - 8), word_at(pos - 4)); pos -= 12; }
+						if (pos - 8 >= M) rem8(word_at(pos - 8), word_at(pos - 4));
+						else if (pos - 4 >= M) rem4(word_at(pos - 4));
+					} else {
+						for (; pos - 3 >= M; pos -= 3) apply3(inv_at(pos - 1) + 12u * inv_at(pos - 2) + 144u * inv_at(pos - 3));
+						if (pos > M) apply_tail(inv_at(pos - 1) + 13u * (pos - 2 >= M ? inv_at(pos - 2) : 12u));
+					}
+					fold();
+				}
+				// two groups (48 moves) per trip: half the loop bookkeeping
 				for (; m >= 24; m -= 48) { group24(m); group24(m - 24); }
 				if (m >= 0) group24(m);
 			}
