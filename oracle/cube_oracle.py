@@ -415,6 +415,35 @@ def bfs_layers(max_depth: int, is2024: bool = True, start: np.ndarray | None = N
 	return counts, seen
 
 
+def bfs_search(start: np.ndarray, max_states: int, is2024: bool = True):
+	"""BFS.search (agents.py:96-123) restated literally: FIFO queue, dict keyed on the state bytes, the budget test
+	`len(states) < max_states` before EVERY parent pop (agents.py:104), children in action order, a solved child ends the
+	search before it is recorded.  Returns (found, len(agent), action queue)."""
+	start = np.asarray(start)
+	if is_solved(start, is2024):
+		return True, 0, []
+	states = {start.tobytes(): (None, None)}
+	queue = [start]
+	head = 0
+	while len(states) < max_states:
+		state = queue[head]; head += 1
+		tstate = state.tobytes()
+		for a in range(12):
+			child = rotate(state, a // 2, 1 - a % 2, is2024)
+			key = child.tobytes()
+			if key in states:
+				continue
+			if is_solved(child, is2024):
+				actions = [a]
+				while states[tstate][0] is not None:
+					actions.insert(0, states[tstate][1])
+					tstate = states[tstate][0]
+				return True, len(states), actions
+			states[key] = (tstate, a)
+			queue.append(child)
+	return False, len(states), []
+
+
 def bfs_layer_counts_packed(max_depth: int) -> list:
 	"""Same counts for the 20x24 representation at scale (depth 7 = 9.2 M states) using
 	sorted 128-bit packed keys instead of a Python dict; used to pin the KAT

@@ -163,9 +163,17 @@ class Agent:
 
 
 class BFS(Agent):
-	"""Breadth-first search (agents.py:92-129), one kernel sequence per layer instead of one dict probe per child.
-	Visits parents in discovery order and children in action order, so the first solved child found, the recorded
-	(parent, action) links and `len(agent)` are those of the reference's FIFO loop."""
+	"""Breadth-first search (agents.py:92-129) as layer-synchronous kernel sequences instead of one dict probe per child.
+
+	The reference pops ONE parent at a time and tests its budget `len(self) < max_states` before every pop (agents.py:104),
+	so a search that runs out of budget stops in the middle of a layer.  Parents are expanded here a slice of the FIFO
+	frontier at a time; new children come back compacted in FIFO order with their parent position, so the parent at which
+	the reference would have stopped is found by position: the last admitted parent is the one that records the
+	(budget)-th new state, every later parent's children are dropped, and a solved child only counts under an admitted
+	parent.  `len(agent)`, the found flag and the action queue are the reference's for any budget
+	(tests/golden/bfs_budget.npz).  The time limit is tested once per slice, not once per parent."""
+
+	_min_slice = 4096                              # parents per expansion when the budget is small
 
 	def __init__(self, is2024: bool | None = None):
 		super().__init__()
@@ -180,26 +188,41 @@ class BFS(Agent):
 		if bool((frontier[0].cpu().numpy() == cube._solved[hs.rep]).all()):
 			return True
 		hs.insert_unique(frontier)
-		total = 1
-		layers = []                                   # per layer: (parent position in previous layer, action)
-		while perf_counter() - t0 < time_limit and total < max_states and frontier.shape[0]:
-			out = hs.expand(frontier, flags=True)
-			n_new = int(out["n_new"].item())
-			solved = out["solved"][:n_new]
-			hit = torch.nonzero(solved)
-			layers.append((out["parent"][:n_new], out["action"][:n_new]))
-			if hit.numel():
-				k = int(hit[0].item())                # first solved new child in batch (= FIFO) order
-				# the reference stops before recording the solved child: the dict holds the states discovered before it
-				self._explored_states = total + k
-				pos = k
-				for parent, action in reversed(layers):
-					self.action_queue.appendleft(int(action[pos].item()))
-					pos = int(parent[pos].item())
-				return True
-			total += n_new
-			self._explored_states = total
-			frontier = out["next"][:n_new]
+		total = self._explored_states = 1
+		layers = []                                   # per layer: (position of the parent in the previous layer, action)
+		while frontier.shape[0] and total < max_states:
+			nxt, par, act, done = [], [], [], 0
+			while done < frontier.shape[0] and total < max_states and perf_counter() - t0 < time_limit:
+				# never more parents than the remaining budget could admit if each recorded a single new state ...
+				take = min(frontier.shape[0] - done, max(self._min_slice, max_states - total))
+				out = hs.expand(frontier[done:done + take])
+				n_new = int(out["n_new"].item())
+				parent = out["parent"][:n_new]
+				n_adm = n_new
+				if total + n_new >= max_states:
+					# ... and the parent that records new state number (max_states - total) is the last one popped
+					last = parent[max_states - total - 1]
+					n_adm = int(torch.searchsorted(parent, last, right=True).item())
+				hit = torch.nonzero(out["solved"][:n_adm])
+				par.append(parent[:n_adm] + done); act.append(out["action"][:n_adm])
+				if hit.numel():
+					k = int(hit[0].item())                # first solved new child in FIFO order
+					# the reference returns before recording it: the dict holds the states discovered before it
+					self._explored_states = total + k
+					layers.append((torch.cat(par), torch.cat(act)))
+					pos = sum(p.shape[0] for p in par[:-1]) + k
+					for parent, action in reversed(layers):
+						self.action_queue.appendleft(int(action[pos].item()))
+						pos = int(parent[pos].item())
+					return True
+				total += n_adm
+				self._explored_states = total
+				nxt.append(out["next"][:n_adm])
+				done += take
+			if done < frontier.shape[0]:
+				return False                              # budget or time ran out inside the layer
+			layers.append((torch.cat(par), torch.cat(act)))
+			frontier = torch.cat(nxt)
 		return False
 
 	def __str__(self):

@@ -293,6 +293,41 @@ def gen_search():
 	save("search", **out)
 
 
+def gen_bfs_budget():
+	"""BFS.search (agents.py:96-123) with a BINDING state budget: the reference tests `len(self) < max_states` before every
+	parent pop (agents.py:104), so a search that runs out of budget stops in the middle of a layer.  Records found flag,
+	len(agent) and the action queue for scrambles of depth 3-6 under budgets that end the search at every stage (first layer,
+	mid layer, exactly on a parent boundary, solved child just inside / just outside the admitted parents)."""
+	cube.set_is2024(True)
+	out, case = {}, 0
+	for depth in (3, 4, 5, 6):
+		for seed in (0, 1, 2):
+			np.random.seed(1000 * depth + seed)
+			state, _, _ = cube.scramble(depth, True)
+			for max_states in (1, 2, 13, 14, 50, 100, 127, 1000, 1195, 2000, 5000, 20000):
+				bfs = agents.BFS()
+				ok = bfs.search(state, None, max_states)
+				out[f"start_{case}"], out[f"max_{case}"] = state, np.int64(max_states)
+				out[f"found_{case}"], out[f"len_{case}"] = np.bool_(ok), np.int64(len(bfs))
+				out[f"queue_{case}"] = np.array(bfs.action_queue, dtype=np.int64)
+				case += 1
+	# 6x8x6: same loop through cube.* under the other representation
+	cube.set_is2024(False)
+	for seed, depth in ((0, 3), (1, 4)):
+		np.random.seed(77 + seed)
+		state, _, _ = cube.scramble(depth, True)
+		for max_states in (14, 100, 1000, 3000):
+			bfs = agents.BFS()
+			ok = bfs.search(state, None, max_states)
+			out[f"start_{case}"], out[f"max_{case}"] = state, np.int64(max_states)
+			out[f"found_{case}"], out[f"len_{case}"] = np.bool_(ok), np.int64(len(bfs))
+			out[f"queue_{case}"] = np.array(bfs.action_queue, dtype=np.int64)
+			case += 1
+	cube.set_is2024(True)
+	out["n_cases"] = np.int64(case)
+	save("bfs_budget", **out)
+
+
 def gen_train():
 	"""Train.train (train.py:111-247) run end to end on the CPU with a narrowed fc net (same layer pattern as fc_small,
 	model.py:117-161, sizes 480 -> 64 -> 32 -> {16 -> 12, 16 -> 1} so that the initial weights fit a fixture): the per-rollout
@@ -347,6 +382,6 @@ def gen_eval():
 
 if __name__ == "__main__":
 	torch.manual_seed(0)
-	which = sys.argv[1:] or ["tables", "dynamics", "scramblers", "adi", "search", "train", "eval"]
+	which = sys.argv[1:] or ["tables", "dynamics", "scramblers", "adi", "search", "bfs_budget", "train", "eval"]
 	for name in which:
 		globals()["gen_" + name]()

@@ -90,6 +90,41 @@ def test_bfs_agent_matches_reference(golden):
 	assert BFS().search(cube.get_solved(), None, 10) is True
 
 
+def test_bfs_agent_budget_limited_matches_reference(golden):
+	"""agents.py:104 tests the budget before every parent pop: found flag, len(agent) and the action queue recorded from the
+	reference under binding budgets (1 ... 20000 states on depth 3-6 scrambles, both representations)."""
+	from rl_rubiks_b200 import cube
+	from rl_rubiks_b200.frontier import BFS
+	g = golden("bfs_budget")
+	for slice_ in (4096, 7):                                   # 7: every layer is expanded in many slices
+		for c in range(int(g["n_cases"])):
+			start, max_states = g[f"start_{c}"], int(g[f"max_{c}"])
+			if slice_ == 7 and max_states > 2000:
+				continue
+			cube.set_is2024(start.shape == (20,))
+			agent = BFS()
+			agent._min_slice = slice_
+			found = agent.search(start, None, max_states)
+			assert found == bool(g[f"found_{c}"]), (c, slice_)
+			assert len(agent) == int(g[f"len_{c}"]), (c, slice_, len(agent), int(g[f"len_{c}"]))
+			assert list(agent.action_queue) == g[f"queue_{c}"].tolist(), (c, slice_)
+	cube.set_is2024(True)
+
+
+def test_bfs_depth7_known_answer():
+	"""BASELINE configs[4] / SURVEY 8c KAT (i): the depth-7 closure from solved has 8 221 632 new states in its last layer
+	(OEIS A080583) and 9 205 558 in total; every one of the 11 807 112 generated children is accounted for."""
+	from rl_rubiks_b200.frontier import bfs_layers
+	counts, hs = bfs_layers(7, is2024=True, capacity=1 << 25)
+	assert counts == [1, 12, 114, 1068, 10011, 93840, 878880, 8221632]
+	assert len(hs) == 9205558
+	# the closure is closed under lookups: the 12 neighbours of the depth-6 states are all in the set
+	from rl_rubiks_b200 import cube
+	acts = np.random.RandomState(0).randint(0, 12, (5000, 6)).astype(np.uint8)
+	inner = cube.scramble_batch(acts)
+	assert (hs.lookup(cube.expand12(inner)) > 0).all()
+
+
 class _FakeNet(torch.nn.Module):
 	def __init__(self, w, quant=4.0):
 		super().__init__()

@@ -218,6 +218,19 @@ def test_bfs_agent_len(golden):
 	assert len(seen) == int(g["bfs_len"]) and queue == g["bfs_queue"].tolist()
 
 
+def test_bfs_search_budget_limited(golden):
+	"""agents.py:104: the budget is tested before every parent pop -- found flag, len(agent) and the action queue recorded
+	from the reference under binding budgets (tests/golden/make_golden.py gen_bfs_budget), both representations."""
+	g = golden("bfs_budget")
+	n = int(g["n_cases"])
+	for c in range(0, n, 1):
+		start, max_states = g[f"start_{c}"], int(g[f"max_{c}"])
+		if max_states > 6000 and c % 3:                       # the slow Python loop: every third of the large budgets
+			continue
+		found, length, queue = O.bfs_search(start, max_states, start.shape == (20,))
+		assert found == bool(g[f"found_{c}"]) and length == int(g[f"len_{c}"]) and queue == g[f"queue_{c}"].tolist(), c
+
+
 @pytest.mark.parametrize("tag,is2024", [("2024", True), ("686", False)])
 def test_astar_expand_batch_trace(golden, tag, is2024):
 	g = golden("search")
