@@ -234,26 +234,62 @@ def run_gpu(args):
 	sub = torch.arange(0, n, max(1, n // 2048), device=dev)[:2048]
 	f, d = O.indices_to_actions(actions[sub].cpu().numpy())
 	parity_ok = bool((out[sub].cpu().numpy() == O.scramble_many(f, d, True)).all())
+	out_ref = out[:4096].cpu().numpy()
 
-	# ---- end to end: host buffers through the C-ABI call, copies inside the timed region ----
-	host_actions = torch.empty(n, depth, dtype=torch.uint8, pin_memory=True)
-	host_actions.copy_(actions)
+	# ---- end to end: host buffers through the C-ABI calls, copies inside the timed region ----
+	# (a) rbh_scramble_seeded: the reference's own call shape -- cube.scramble draws its moves itself (cube.py:206-211), so the
+	#     inputs are (seed, first cube, n, depth) and the results come back as int8[n][20]: 20 B per cube over PCIe.  HEADLINE e2e.
+	# (b) rbh_scramble: host-drawn actions uint8[n][100] in, states out: 120 B per cube over PCIe.
+	# (c) rbh_scramble_packed: host-drawn actions, two moves per byte: 70 B per cube over PCIe.
 	host_out = torch.empty(n, 20, dtype=torch.int8, pin_memory=True)
 	e2e_steps = max(1, min(args.steps, 5))
-	N.check(N.lib.rbh_scramble(N.REP_2024, N.ptr(host_actions), N.ptr(host_out), n, depth))
+	seed, first_cube = 20241018, rank * n                      # rank r owns cubes [r n, (r + 1) n) of ONE stream: no collective
+
+	def timed_e2e(call):
+		N.check(call())
+		barrier()
+		t0 = time.perf_counter()
+		for _ in range(e2e_steps):
+			N.check(call())
+		barrier()
+		te = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+		if world > 1:
+			dist.all_reduce(te, op=dist.ReduceOp.MAX)
+		return float(te.item())
+
+	seeded_s = timed_e2e(lambda: N.lib.rbh_scramble_seeded(N.REP_2024, seed, first_cube, N.ptr(host_out), n, depth))
+	# parity of what was just timed: replay the dumped moves of a subsample on the oracle
+	sub_n = 2048
+	sub_first = first_cube + (n - sub_n)
+	sub_actions = cube.seeded_actions(sub_n, depth, seed, sub_first).cpu().numpy()
+	assert (sub_actions == O.seeded_actions(seed, sub_first, sub_n, depth)).all()
+	f, d = O.indices_to_actions(sub_actions)
+	seeded_ok = bool((host_out[n - sub_n:].numpy() == O.scramble_many(f, d, True)).all())
+	# device-timed seeded kernel alone (20 B per cube leave the chip)
+	for _ in range(3):
+		N.check(N.lib.rb_scramble_seeded(N.REP_2024, seed, first_cube, None, N.ptr(out), n, depth, stream))
+	sa, sb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 	barrier()
-	t0 = time.perf_counter()
-	for _ in range(e2e_steps):
-		N.check(N.lib.rbh_scramble(N.REP_2024, N.ptr(host_actions), N.ptr(host_out), n, depth))
+	sa.record()
+	for _ in range(args.steps):
+		N.check(N.lib.rb_scramble_seeded(N.REP_2024, seed, first_cube, None, N.ptr(out), n, depth, stream))
+	sb.record()
 	barrier()
-	e2e_s = (time.perf_counter() - t0) / e2e_steps
-	te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+	ts = torch.tensor([sa.elapsed_time(sb) / args.steps], dtype=torch.float64, device=dev)
 	if world > 1:
-		dist.all_reduce(te, op=dist.ReduceOp.MAX)
-	e2e_value = world * n * depth / float(te.item())
-	e2e_ok = bool((host_out[:4096].numpy() == out[:4096].cpu().numpy()).all())
+		dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+	seeded_kernel_ms = float(ts.item())
+
+	host_actions = torch.empty(n, depth, dtype=torch.uint8, pin_memory=True)
+	host_actions.copy_(actions)
+	host_s = timed_e2e(lambda: N.lib.rbh_scramble(N.REP_2024, N.ptr(host_actions), N.ptr(host_out), n, depth))
+	e2e_ok = bool((host_out[:4096].numpy() == out_ref[:4096]).all())
+	host_packed = torch.empty(n, depth // 2, dtype=torch.uint8, pin_memory=True)
+	host_packed.copy_(actions[:, 0::2] + 13 * actions[:, 1::2])
+	packed_s = timed_e2e(lambda: N.lib.rbh_scramble_packed(N.REP_2024, N.ptr(host_packed), N.ptr(host_out), n, depth))
+	packed_ok = bool((host_out[:4096].numpy() == out_ref[:4096]).all())
 	N.check(N.lib.rbh_release())
-	del host_actions, host_out
+	del host_actions, host_out, host_packed
 
 	# ---- secondary: fused ADI generator at BASELINE configs[0] (1000 games x depth 25, lapanfix) ----
 	games, adepth = 1000, 25
@@ -314,11 +350,22 @@ def run_gpu(args):
 								 "source": "ncu --set full, profiles/r1q_scramble_macro3_ncu.txt"}},
 		"cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
 						 "sample": f"{cores} processes x {cpu_chunks * CPU_CHUNK} cubes x {depth} moves, numpy oracle port, {cpu_dt:.1f} s"},
-		"e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * depth, "d2h_bytes_per_step": n * 20,
-				"ms_per_step": float(te.item()) * 1e3, "api": "rbh_scramble (C ABI, pinned host buffers)", "parity_ok": e2e_ok},
+		"e2e": {"value": world * n * depth / seeded_s, "unit": UNIT, "h2d_bytes_per_step": 16, "d2h_bytes_per_step": n * 20,
+				"ms_per_step": seeded_s * 1e3, "parity_ok": seeded_ok,
+				"api": "rbh_scramble_seeded (C ABI): the moves are drawn on the device (Philox4x32-10, one subsequence per cube) as cube.scramble "
+					   "draws its own (cube.py:206-211); in: seed + first cube id (16 B), out: int8[n][20] to pinned host memory",
+				"algorithmic_bytes_per_cube": 20,
+				"host_actions": {"value": world * n * depth / host_s, "ms_per_step": host_s * 1e3, "h2d_bytes_per_step": n * depth,
+								 "d2h_bytes_per_step": n * 20, "api": "rbh_scramble: host-drawn uint8[n][100] actions in", "parity_ok": e2e_ok,
+								 "algorithmic_bytes_per_cube": 120},
+				"packed_actions": {"value": world * n * depth / packed_s, "ms_per_step": packed_s * 1e3, "h2d_bytes_per_step": n * depth // 2,
+								   "d2h_bytes_per_step": n * 20, "api": "rbh_scramble_packed: host-drawn actions, two moves per byte", "parity_ok": packed_ok,
+								   "algorithmic_bytes_per_cube": 70}},
 		"gpu_launches": int(launches),
 		"clocks": clocks.summary(),
-		"extra": {"adi": {"workload": "fused ADI batch 1000 games x depth 25 (BASELINE configs[0]): generate + targets kernels",
+		"extra": {"seeded_kernel": {"workload": "rb_scramble_seeded, device-resident: Philox draw + scramble in one kernel, 20 B per cube written",
+									"moves_per_sec": world * n * depth / (seeded_kernel_ms * 1e-3), "ms": seeded_kernel_ms},
+				  "adi": {"workload": "fused ADI batch 1000 games x depth 25 (BASELINE configs[0]): generate + targets kernels",
 						  "samples_per_sec": nst / adi_t, "children_per_sec": 12 * nst / adi_t, "ms": adi_t * 1e3,
 						  "roofline": {"bound": "hbm", "achieved": adi_bytes / adi_t / 1e9, "peak": peak, "unit": "GB/s",
 									   "frac": adi_bytes / adi_t / 1e9 / peak, "algorithmic_bytes": adi_bytes},

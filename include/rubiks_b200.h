@@ -110,6 +110,21 @@ int rb_scramble(int rep, const uint8_t* actions, int64_t stride_cube, int64_t st
 int rb_sequence_scramble(int rep, const uint8_t* faces, const uint8_t* dirs, int32_t games, int32_t depth,
                          int32_t with_solved, int8_t* states, float* oh, uint8_t* solved, rb_stream_t stream);
 
+/* scramble with the random draw made ON the device (cube.py:206-211 for n cubes: `depth` moves per cube, every move uniform over
+ * the 12 actions; SURVEY 8d C2 "generate on device from the same counter-based stream").  Cube i uses subsequence
+ * first_cube + i of the Philox4x32-10 stream keyed by `seed` (csrc/rb_scramble_seeded.cuh defines word -> moves), so the result
+ * for a cube does not depend on how the cubes are split over calls, streams or GPUs.  No action bytes are read: 20 (288) B per
+ * cube leave the chip.  start: optional start states as for rb_scramble. */
+int rb_scramble_seeded(int rep, uint64_t seed, uint64_t first_cube, const int8_t* start, int8_t* out, int64_t n,
+                       int32_t depth, rb_stream_t stream);
+/* The same stream written out as action indices, uint8 [n][depth]: what rb_scramble_seeded applied to cube i.  (Parity of the
+ * seeded path = these bytes replayed through the reference's own rotate loop.) */
+int rb_seeded_actions(uint64_t seed, uint64_t first_cube, uint8_t* actions, int64_t n, int32_t depth, rb_stream_t stream);
+/* Packed actions: two moves per byte, p = a(2k) + 13 * a(2k+1), a second digit of 12 = "no move" (last byte of an odd-depth
+ * row) -- the row index of the 2-move table (rb_get_macro_table).  packed uint8 [n][(depth + 1) / 2] -> actions uint8 [n][depth].
+ * Halves the host->device bytes of a host-drawn scramble (rbh_scramble_packed). */
+int rb_unpack_actions(const uint8_t* packed, uint8_t* actions, int64_t n, int32_t depth, rb_stream_t stream);
+
 /* ---- ADI training batch (librubiks/train.py:256-339) --------------------------------------- */
 /* Fused generator, train.py:277-296 in one launch: sequence scramble -> 12 children of every state ->
  * one-hot of states and of children -> solved flags of both.  n = games*depth.
@@ -224,6 +239,10 @@ int rb_astar_commit(const rb_astar_view* v, const float* values, double lambda, 
 /* rb_scramble on host buffers; actions uint8 [n][depth] (cube-major), out int8 [n][*shape].  Copies are
  * chunked and double-buffered on internal streams; pinned host memory makes them asynchronous. */
 int rbh_scramble(int rep, const uint8_t* actions, int8_t* out, int64_t n, int32_t depth);
+/* rbh_scramble with packed actions (see rb_unpack_actions): half the bytes over PCIe. */
+int rbh_scramble_packed(int rep, const uint8_t* packed, int8_t* out, int64_t n, int32_t depth);
+/* rb_scramble_seeded into a host buffer: nothing but the seed goes to the device, 20 (288) B per cube come back. */
+int rbh_scramble_seeded(int rep, uint64_t seed, uint64_t first_cube, int8_t* out, int64_t n, int32_t depth);
 /* multi_rotate on host buffers (the reference's own call shape: numpy in, numpy out). */
 int rbh_multi_rotate(int rep, const int8_t* states, const uint8_t* faces, const uint8_t* dirs,
                      int8_t* out, int64_t n);

@@ -304,6 +304,64 @@ def sequence_scrambler(faces: np.ndarray, directions: np.ndarray, with_solved: b
 
 
 # ---------------------------------------------------------------------------
+# Device-seeded scramble stream (no reference analogue beyond the distribution of cube.py:208-209: every move uniform over
+# 6 faces x 2 directions).  The generator is Philox4x32-10 (Salmon et al., SC'11; Random123 / cuRAND), restated here from the
+# paper and pinned on the Random123 known-answer vectors (tests/test_oracle_golden.py); the word -> moves rule is the one
+# csrc/rb_scramble_seeded.cuh documents.
+# ---------------------------------------------------------------------------
+_PHILOX_M0, _PHILOX_M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+_PHILOX_W0, _PHILOX_W1 = 0x9E3779B9, 0xBB67AE85
+
+
+def philox4x32_10(counter: np.ndarray, key) -> np.ndarray:
+	"""counter: uint32 (n, 4); key: (k0, k1).  Returns uint32 (n, 4).  Ten rounds of
+	(c0, c1, c2, c3) <- (hi(M1*c2) ^ c1 ^ k0, lo(M1*c2), hi(M0*c0) ^ c3 ^ k1, lo(M0*c0)), the key bumped by the Weyl constants
+	between rounds."""
+	c = np.asarray(counter, dtype=np.uint64).copy()
+	k0, k1 = int(key[0]) & 0xffffffff, int(key[1]) & 0xffffffff
+	mask = np.uint64(0xffffffff)
+	for _ in range(10):
+		p0, p1 = _PHILOX_M0 * c[:, 0], _PHILOX_M1 * c[:, 2]
+		n0 = (p1 >> np.uint64(32)) ^ c[:, 1] ^ np.uint64(k0)
+		n2 = (p0 >> np.uint64(32)) ^ c[:, 3] ^ np.uint64(k1)
+		c = np.stack([n0, p1 & mask, n2, p0 & mask], axis=1)
+		k0, k1 = (k0 + _PHILOX_W0) & 0xffffffff, (k1 + _PHILOX_W1) & 0xffffffff
+	return c.astype(np.uint32)
+
+
+def seeded_actions(seed: int, first_cube: int, n: int, depth: int) -> np.ndarray:
+	"""Action indices uint8 (n, depth) of the device-seeded stream: cube i = Philox subsequence first_cube + i (counter words
+	2, 3), block j = counter word 0; output word k of block j is triple q = 4 j + k; t = (word * 1728) >> 32;
+	moves 3q, 3q+1, 3q+2 = t // 144, t // 12 % 12, t % 12."""
+	n_triples = (depth + 2) // 3
+	n_blocks = (n_triples + 3) // 4
+	cube = (np.arange(n, dtype=np.uint64) + np.uint64(first_cube & 0xffffffffffffffff))
+	out = np.empty((n, n_blocks * 12), dtype=np.uint8)
+	for j in range(n_blocks):
+		ctr = np.stack([np.full(n, j, np.uint64), np.zeros(n, np.uint64), cube & np.uint64(0xffffffff), cube >> np.uint64(32)], axis=1)
+		words = philox4x32_10(ctr, (seed & 0xffffffff, (seed >> 32) & 0xffffffff)).astype(np.uint64)
+		t = (words * np.uint64(1728)) >> np.uint64(32)
+		blk = np.stack([t // 144, t // 12 % 12, t % 12], axis=2).reshape(n, 12)
+		out[:, 12 * j:12 * j + 12] = blk
+	return np.ascontiguousarray(out[:, :depth])
+
+
+def pack_actions(actions: np.ndarray) -> np.ndarray:
+	"""uint8 (n, depth) action indices -> packed uint8 (n, (depth+1)//2): p = a(2k) + 13 * a(2k+1), 12 = no second move."""
+	a = np.asarray(actions, dtype=np.uint8)
+	n, depth = a.shape
+	if depth % 2:
+		a = np.concatenate([a, np.full((n, 1), 12, np.uint8)], axis=1)
+	return (a[:, 0::2] + 13 * a[:, 1::2]).astype(np.uint8)
+
+
+def unpack_actions(packed: np.ndarray, depth: int) -> np.ndarray:
+	p = np.asarray(packed, dtype=np.uint8)
+	a = np.stack([p % 13, p // 13], axis=2).reshape(len(p), -1)
+	return np.ascontiguousarray(a[:, :depth])
+
+
+# ---------------------------------------------------------------------------
 # ADI training-batch assembly.  Reference: librubiks/train.py:256-339.
 # ---------------------------------------------------------------------------
 REWARD_METHODS = ("paper", "lapanfix", "schultzfix", "reward0")

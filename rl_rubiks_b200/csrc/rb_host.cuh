@@ -19,59 +19,117 @@ k_check_range(int rep, const uint8_t* __restrict__ states, int64_t n_state_bytes
 	if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
 }
 
+// Packed actions -> action bytes.  Packed byte p = a0 + 13 * a1 holds moves (2k, 2k + 1) of a cube (a1 = 12: no second move, only
+// in the last byte of an odd-depth row) -- the row index of the 2-move table (rb_get_macro_table).  Rows: packed [n][(depth + 1) / 2],
+// actions [n][depth].  Even depth is one flat stream: 16 packed bytes in, 32 action bytes out per thread.
+__global__ void __launch_bounds__(256)
+k_unpack_actions(const uint8_t* __restrict__ packed, uint8_t* __restrict__ actions, int64_t n, int depth, int vec_ok) {
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const int pb = (depth + 1) >> 1;
+	auto split = [](uint32_t w, uint32_t& lo, uint32_t& hi) {                 // 4 packed bytes -> 8 action bytes
+		uint32_t a[8];
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			const uint32_t p = (w >> (8 * k)) & 0xffu, q = (p * 79u) >> 10;     // p / 13 for p < 256
+			a[2 * k] = p - 13u * q; a[2 * k + 1] = q;
+		}
+		lo = a[0] | (a[1] << 8) | (a[2] << 16) | (a[3] << 24);
+		hi = a[4] | (a[5] << 8) | (a[6] << 16) | (a[7] << 24);
+	};
+	if (vec_ok) {                                                            // even depth, 16-byte aligned pointers
+		const int64_t total = n * pb, nv = total >> 4;
+		for (int64_t i = t0; i < nv; i += stride) {
+			const uint4 v = rb_ld_stream(reinterpret_cast<const uint4*>(packed) + i);
+			uint4 o0, o1;
+			split(v.x, o0.x, o0.y); split(v.y, o0.z, o0.w); split(v.z, o1.x, o1.y); split(v.w, o1.z, o1.w);
+			reinterpret_cast<uint4*>(actions)[2 * i] = o0;
+			reinterpret_cast<uint4*>(actions)[2 * i + 1] = o1;
+		}
+		for (int64_t i = (nv << 4) + t0; i < total; i += stride) {
+			const uint32_t p = packed[i], q = (p * 79u) >> 10;
+			actions[2 * i] = (uint8_t)(p - 13u * q); actions[2 * i + 1] = (uint8_t)q;
+		}
+		return;
+	}
+	const int64_t total = n * pb;
+	for (int64_t i = t0; i < total; i += stride) {
+		const int64_t c = i / pb;
+		const int k = (int)(i - c * pb);
+		const uint32_t p = packed[i], q = (p * 79u) >> 10;
+		actions[c * depth + 2 * k] = (uint8_t)(p - 13u * q);
+		if (2 * k + 1 < depth) actions[c * depth + 2 * k + 1] = (uint8_t)q;
+	}
+}
+
 // Device staging for the host-buffer entry points: two slots so that the H2D copy of chunk k+1, the kernel on
 // chunk k and the D2H copy of chunk k-1 overlap.  Grown on demand, released by rbh_release().
 struct Staging {
-	void* in[2] = {nullptr, nullptr};
-	void* in2[2] = {nullptr, nullptr};
-	void* out[2] = {nullptr, nullptr};
-	size_t in_bytes = 0, in2_bytes = 0, out_bytes = 0;
+	void* buf[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};   // per slot: in, in2, out, scratch
+	size_t bytes[4] = {0, 0, 0, 0};
 	cudaStream_t stream[2] = {nullptr, nullptr};
 	int device = -1;
 };
 static Staging g_stage;
 static std::mutex g_stage_mu;
 
-static int stage_reserve(size_t in_bytes, size_t in2_bytes, size_t out_bytes) {
+// Frees every buffer and stream on the device that owns them; pointers are nulled and sizes zeroed BEFORE anything can fail.
+static void stage_drop(Staging& s) {
+	int cur = -1;
+	if (s.device >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != s.device) cudaSetDevice(s.device);
+	for (int k = 0; k < 2; ++k) {
+		for (int b = 0; b < 4; ++b) {
+			void* p = s.buf[k][b];
+			s.buf[k][b] = nullptr;
+			if (p) cudaFree(p);
+		}
+		cudaStream_t st = s.stream[k];
+		s.stream[k] = nullptr;
+		if (st) cudaStreamDestroy(st);
+	}
+	for (int b = 0; b < 4; ++b) s.bytes[b] = 0;
+	if (cur >= 0 && cur != s.device) cudaSetDevice(cur);
+	s.device = -1;
+}
+
+static int stage_reserve(size_t in_bytes, size_t in2_bytes, size_t out_bytes, size_t scratch_bytes = 0) {
 	int dev = 0;
 	RB_CUDA(cudaGetDevice(&dev));
 	Staging& s = g_stage;
 	if (s.device != dev) {
-		for (int k = 0; k < 2; ++k) {
-			if (s.in[k]) cudaFree(s.in[k]);
-			if (s.in2[k]) cudaFree(s.in2[k]);
-			if (s.out[k]) cudaFree(s.out[k]);
-			if (s.stream[k]) cudaStreamDestroy(s.stream[k]);
-			s.in[k] = s.in2[k] = s.out[k] = nullptr;
-			s.stream[k] = nullptr;
-		}
-		s.in_bytes = s.in2_bytes = s.out_bytes = 0;
+		stage_drop(s);
 		s.device = dev;
 	}
-	for (int k = 0; k < 2; ++k) {
+	const size_t want[4] = {in_bytes, in2_bytes, out_bytes, scratch_bytes};
+	for (int k = 0; k < 2; ++k)
 		if (!s.stream[k]) RB_CUDA(cudaStreamCreateWithFlags(&s.stream[k], cudaStreamNonBlocking));
-		if (in_bytes > s.in_bytes) { if (s.in[k]) cudaFree(s.in[k]); RB_CUDA(cudaMalloc(&s.in[k], in_bytes)); }
-		if (in2_bytes > s.in2_bytes) { if (s.in2[k]) cudaFree(s.in2[k]); RB_CUDA(cudaMalloc(&s.in2[k], in2_bytes)); }
-		if (out_bytes > s.out_bytes) { if (s.out[k]) cudaFree(s.out[k]); RB_CUDA(cudaMalloc(&s.out[k], out_bytes)); }
+	for (int b = 0; b < 4; ++b) {
+		if (want[b] <= s.bytes[b]) continue;
+		s.bytes[b] = 0;                                    // a failed allocation leaves "nothing reserved", never a dangling pointer
+		for (int k = 0; k < 2; ++k) {
+			void* p = s.buf[k][b];
+			s.buf[k][b] = nullptr;
+			if (p) RB_CUDA(cudaFree(p));
+		}
+		for (int k = 0; k < 2; ++k) RB_CUDA(cudaMalloc(&s.buf[k][b], want[b]));
+		s.bytes[b] = want[b];
 	}
-	if (in_bytes > s.in_bytes) s.in_bytes = in_bytes;
-	if (in2_bytes > s.in2_bytes) s.in2_bytes = in2_bytes;
-	if (out_bytes > s.out_bytes) s.out_bytes = out_bytes;
 	return RB_OK;
 }
 
-static int stage_release() {
+// Waits for both staging streams (used on every exit path of an rbh_* call: no copy to or from the caller's host buffers may
+// still be in flight when the call returns) and reports the first error.
+static int stage_sync(int rc) {
 	Staging& s = g_stage;
 	for (int k = 0; k < 2; ++k) {
-		if (s.in[k]) cudaFree(s.in[k]);
-		if (s.in2[k]) cudaFree(s.in2[k]);
-		if (s.out[k]) cudaFree(s.out[k]);
-		if (s.stream[k]) cudaStreamDestroy(s.stream[k]);
-		s.in[k] = s.in2[k] = s.out[k] = nullptr;
-		s.stream[k] = nullptr;
+		if (!s.stream[k]) continue;
+		const cudaError_t e = cudaStreamSynchronize(s.stream[k]);
+		if (e != cudaSuccess && rc == RB_OK) rc = rb_fail(RB_ERR_CUDA, "%s: %s", "cudaStreamSynchronize(staging stream)", cudaGetErrorString(e));
 	}
-	s.in_bytes = s.in2_bytes = s.out_bytes = 0;
-	s.device = -1;
+	return rc;
+}
+
+static int stage_release() {
+	stage_drop(g_stage);
 	return RB_OK;
 }
 

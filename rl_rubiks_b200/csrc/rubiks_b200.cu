@@ -3,6 +3,7 @@
 #include "rb_tables.cuh"
 #include "rb_cube2024.cuh"
 #include "rb_scramble_macro.cuh"
+#include "rb_scramble_seeded.cuh"
 #include "rb_cube686.cuh"
 #include "rb_adi.cuh"
 #include "rb_frontier.cuh"
@@ -592,35 +593,125 @@ int rb_astar_commit(const rb_astar_view* a, const float* values, double lambda, 
 	return RB_OK;
 }
 
+// ---- device-seeded and packed scrambles --------------------------------------------------------------------------------------
+int rb_scramble_seeded(int rep, uint64_t seed, uint64_t first_cube, const int8_t* start, int8_t* out, int64_t n, int32_t depth,
+                       rb_stream_t stream) {
+	RB_REQUIRE(rep_ok(rep) && n >= 0 && depth >= 0, "bad rep or size");
+	if (n == 0) return RB_OK;
+	RB_REQUIRE(out && start != out, "null output (or start aliases out)");
+	RB_INIT();
+	if (rep == RB_REP_2024) {
+		int rc = rbs::launch_seeded(seed, first_cube, out, n, depth, S(stream));
+		if (rc != RB_OK || !start) return rc;
+		rb2024::k_compose<<<rb_grid(n, 8, 8), rb2024::kThreads, 0, S(stream)>>>(out, start, n);       // start, then the sequence
+		RB_LAUNCHED("compose_2024");
+		return RB_OK;
+	}
+	RB_REQUIRE(aligned(out, 16) && aligned(start, 16), "6x8x6 states must be 16-byte aligned");
+	RB_REQUIRE(rbt::host().stickers_ok, "sticker tables: the 20x24 and 6x8x6 move tables disagree");
+	int rc = rbs::launch_seeded(seed, first_cube, out, n, depth, S(stream), rb686::kStateBytes);    // 20x24 state parked at the row head
+	if (rc != RB_OK) return rc;
+	rb686::k_render_from2024<<<rb_grid((n + 31) / 32, rb686::kWarps, 8), rb686::kThreads, 0, S(stream)>>>(out, start, n);
+	RB_LAUNCHED("render_686");
+	return RB_OK;
+}
+
+int rb_seeded_actions(uint64_t seed, uint64_t first_cube, uint8_t* actions, int64_t n, int32_t depth, rb_stream_t stream) {
+	RB_REQUIRE(n >= 0 && depth >= 0, "bad size");
+	if (n == 0 || depth == 0) return RB_OK;
+	RB_REQUIRE(actions, "null output");
+	return rbs::launch_seeded_actions(seed, first_cube, actions, n, depth, S(stream));
+}
+
+int rb_unpack_actions(const uint8_t* packed, uint8_t* actions, int64_t n, int32_t depth, rb_stream_t stream) {
+	RB_REQUIRE(n >= 0 && depth >= 0, "bad size");
+	if (n == 0 || depth == 0) return RB_OK;
+	RB_REQUIRE(packed && actions, "null pointer");
+	const int vec_ok = depth % 2 == 0 && aligned(packed, 16) && aligned(actions, 16);
+	const int64_t work = n * ((depth + 1) / 2);
+	rbh::k_unpack_actions<<<rb_grid(vec_ok ? work / 16 + 1 : work, 256, 8), 256, 0, S(stream)>>>(packed, actions, n, depth, vec_ok);
+	RB_LAUNCHED("unpack_actions");
+	return RB_OK;
+}
+
 // ---- host-buffer entry points ------------------------------------------------------------------------------
+extern "C++" {
+// Runs enqueue(slot, stream, base, count) over [0, n) in chunks, alternating the two staging slots; always drains both streams
+// before returning (no copy to or from the caller's host buffers is left in flight, error or not).
+template <class Enqueue>
+static int rbh_run_chunks(int64_t n, int64_t chunk, Enqueue enqueue) {
+	rbh::Staging& st = rbh::g_stage;
+	int rc = RB_OK, k = 0;
+	for (int64_t base = 0; base < n && rc == RB_OK; base += chunk, k ^= 1)
+		rc = enqueue(k, st.stream[k], base, n - base < chunk ? n - base : chunk);
+	return rbh::stage_sync(rc);
+}
+// chunks of <= cap items (a multiple of 256 so every chunk base stays 16-byte aligned), at least 4 chunks
+static int64_t rbh_chunk(int64_t n, int64_t cap) {
+	int64_t chunk = ((n + 3) / 4 + 255) / 256 * 256;
+	return chunk > cap ? cap : chunk;
+}
+}  // extern "C++"
+
 int rbh_scramble(int rep, const uint8_t* actions, int8_t* out, int64_t n, int32_t depth) {
 	RB_REQUIRE(rep_ok(rep) && n >= 0 && depth >= 0, "bad rep or size");
 	if (n == 0) return RB_OK;
 	RB_REQUIRE(out && (actions || depth == 0), "null pointer");
 	RB_INIT();
 	std::lock_guard<std::mutex> lock(rbh::g_stage_mu);
-	const int64_t sb = rep == RB_REP_2024 ? 20 : 288;
-	// chunks of <= 2^20 cubes (a multiple of 256 so every chunk base stays 16-byte aligned), at least 4 chunks
-	int64_t chunk = (n + 3) / 4;
-	chunk = (chunk + 255) / 256 * 256;
-	if (chunk > (1 << 20)) chunk = 1 << 20;
+	const int64_t sb = rep == RB_REP_2024 ? 20 : 288, chunk = rbh_chunk(n, 1 << 20);
 	int rc = rbh::stage_reserve((size_t)chunk * (depth > 0 ? depth : 1), 0, (size_t)chunk * sb);
 	if (rc != RB_OK) return rc;
 	rbh::Staging& st = rbh::g_stage;
-	int k = 0;
-	for (int64_t base = 0; base < n; base += chunk, k ^= 1) {
-		const int64_t cnt = n - base < chunk ? n - base : chunk;
-		cudaStream_t s = st.stream[k];
-		if (depth > 0)
-			RB_CUDA(cudaMemcpyAsync(st.in[k], actions + base * depth, (size_t)cnt * depth, cudaMemcpyHostToDevice, s));
-		rc = rb_scramble(rep, reinterpret_cast<const uint8_t*>(st.in[k]), depth, 1, nullptr, reinterpret_cast<int8_t*>(st.out[k]), cnt,
-		                 depth, s);
-		if (rc != RB_OK) return rc;
-		RB_CUDA(cudaMemcpyAsync(out + base * sb, st.out[k], (size_t)cnt * sb, cudaMemcpyDeviceToHost, s));
-	}
-	RB_CUDA(cudaStreamSynchronize(st.stream[0]));
-	RB_CUDA(cudaStreamSynchronize(st.stream[1]));
-	return RB_OK;
+	return rbh_run_chunks(n, chunk, [&](int k, cudaStream_t s, int64_t base, int64_t cnt) -> int {
+		if (depth > 0) RB_CUDA(cudaMemcpyAsync(st.buf[k][0], actions + base * depth, (size_t)cnt * depth, cudaMemcpyHostToDevice, s));
+		int r = rb_scramble(rep, reinterpret_cast<const uint8_t*>(st.buf[k][0]), depth, 1, nullptr, reinterpret_cast<int8_t*>(st.buf[k][2]), cnt, depth, s);
+		if (r != RB_OK) return r;
+		RB_CUDA(cudaMemcpyAsync(out + base * sb, st.buf[k][2], (size_t)cnt * sb, cudaMemcpyDeviceToHost, s));
+		return RB_OK;
+	});
+}
+
+int rbh_scramble_packed(int rep, const uint8_t* packed, int8_t* out, int64_t n, int32_t depth) {
+	RB_REQUIRE(rep_ok(rep) && n >= 0 && depth >= 0, "bad rep or size");
+	if (n == 0) return RB_OK;
+	RB_REQUIRE(out && (packed || depth == 0), "null pointer");
+	RB_INIT();
+	std::lock_guard<std::mutex> lock(rbh::g_stage_mu);
+	const int64_t sb = rep == RB_REP_2024 ? 20 : 288, pb = (depth + 1) / 2, chunk = rbh_chunk(n, 1 << 20);
+	int rc = rbh::stage_reserve((size_t)chunk * (pb > 0 ? pb : 1), 0, (size_t)chunk * sb, (size_t)chunk * (depth > 0 ? depth : 1));
+	if (rc != RB_OK) return rc;
+	rbh::Staging& st = rbh::g_stage;
+	return rbh_run_chunks(n, chunk, [&](int k, cudaStream_t s, int64_t base, int64_t cnt) -> int {
+		uint8_t* acts = reinterpret_cast<uint8_t*>(st.buf[k][3]);
+		if (depth > 0) {
+			RB_CUDA(cudaMemcpyAsync(st.buf[k][0], packed + base * pb, (size_t)cnt * pb, cudaMemcpyHostToDevice, s));
+			int r = rb_unpack_actions(reinterpret_cast<const uint8_t*>(st.buf[k][0]), acts, cnt, depth, s);
+			if (r != RB_OK) return r;
+		}
+		int r = rb_scramble(rep, acts, depth, 1, nullptr, reinterpret_cast<int8_t*>(st.buf[k][2]), cnt, depth, s);
+		if (r != RB_OK) return r;
+		RB_CUDA(cudaMemcpyAsync(out + base * sb, st.buf[k][2], (size_t)cnt * sb, cudaMemcpyDeviceToHost, s));
+		return RB_OK;
+	});
+}
+
+int rbh_scramble_seeded(int rep, uint64_t seed, uint64_t first_cube, int8_t* out, int64_t n, int32_t depth) {
+	RB_REQUIRE(rep_ok(rep) && n >= 0 && depth >= 0, "bad rep or size");
+	if (n == 0) return RB_OK;
+	RB_REQUIRE(out, "null pointer");
+	RB_INIT();
+	std::lock_guard<std::mutex> lock(rbh::g_stage_mu);
+	const int64_t sb = rep == RB_REP_2024 ? 20 : 288, chunk = rbh_chunk(n, 1 << 20);
+	int rc = rbh::stage_reserve(0, 0, (size_t)chunk * sb);
+	if (rc != RB_OK) return rc;
+	rbh::Staging& st = rbh::g_stage;
+	return rbh_run_chunks(n, chunk, [&](int k, cudaStream_t s, int64_t base, int64_t cnt) -> int {
+		int r = rb_scramble_seeded(rep, seed, first_cube + (uint64_t)base, nullptr, reinterpret_cast<int8_t*>(st.buf[k][2]), cnt, depth, s);
+		if (r != RB_OK) return r;
+		RB_CUDA(cudaMemcpyAsync(out + base * sb, st.buf[k][2], (size_t)cnt * sb, cudaMemcpyDeviceToHost, s));
+		return RB_OK;
+	});
 }
 
 int rbh_multi_rotate(int rep, const int8_t* states, const uint8_t* faces, const uint8_t* dirs, int8_t* out, int64_t n) {
@@ -629,29 +720,21 @@ int rbh_multi_rotate(int rep, const int8_t* states, const uint8_t* faces, const 
 	RB_REQUIRE(states && faces && out, "null pointer");
 	RB_INIT();
 	std::lock_guard<std::mutex> lock(rbh::g_stage_mu);
-	const int64_t sb = rep == RB_REP_2024 ? 20 : 288;
-	int64_t chunk = (n + 3) / 4;
-	chunk = (chunk + 255) / 256 * 256;
-	if (chunk > (1 << 22)) chunk = 1 << 22;
+	const int64_t sb = rep == RB_REP_2024 ? 20 : 288, chunk = rbh_chunk(n, 1 << 22);
 	int rc = rbh::stage_reserve((size_t)chunk * sb, (size_t)chunk * 2, (size_t)chunk * sb);
 	if (rc != RB_OK) return rc;
 	rbh::Staging& st = rbh::g_stage;
-	int k = 0;
-	for (int64_t base = 0; base < n; base += chunk, k ^= 1) {
-		const int64_t cnt = n - base < chunk ? n - base : chunk;
-		cudaStream_t s = st.stream[k];
-		uint8_t* f_dev = reinterpret_cast<uint8_t*>(st.in2[k]);
+	return rbh_run_chunks(n, chunk, [&](int k, cudaStream_t s, int64_t base, int64_t cnt) -> int {
+		uint8_t* f_dev = reinterpret_cast<uint8_t*>(st.buf[k][1]);
 		uint8_t* d_dev = dirs ? f_dev + chunk : nullptr;
-		RB_CUDA(cudaMemcpyAsync(st.in[k], states + base * sb, (size_t)cnt * sb, cudaMemcpyHostToDevice, s));
+		RB_CUDA(cudaMemcpyAsync(st.buf[k][0], states + base * sb, (size_t)cnt * sb, cudaMemcpyHostToDevice, s));
 		RB_CUDA(cudaMemcpyAsync(f_dev, faces + base, (size_t)cnt, cudaMemcpyHostToDevice, s));
 		if (dirs) RB_CUDA(cudaMemcpyAsync(d_dev, dirs + base, (size_t)cnt, cudaMemcpyHostToDevice, s));
-		rc = rb_multi_rotate(rep, reinterpret_cast<const int8_t*>(st.in[k]), f_dev, d_dev, reinterpret_cast<int8_t*>(st.out[k]), cnt, s);
-		if (rc != RB_OK) return rc;
-		RB_CUDA(cudaMemcpyAsync(out + base * sb, st.out[k], (size_t)cnt * sb, cudaMemcpyDeviceToHost, s));
-	}
-	RB_CUDA(cudaStreamSynchronize(st.stream[0]));
-	RB_CUDA(cudaStreamSynchronize(st.stream[1]));
-	return RB_OK;
+		int r = rb_multi_rotate(rep, reinterpret_cast<const int8_t*>(st.buf[k][0]), f_dev, d_dev, reinterpret_cast<int8_t*>(st.buf[k][2]), cnt, s);
+		if (r != RB_OK) return r;
+		RB_CUDA(cudaMemcpyAsync(out + base * sb, st.buf[k][2], (size_t)cnt * sb, cudaMemcpyDeviceToHost, s));
+		return RB_OK;
+	});
 }
 
 int rbh_release(void) {

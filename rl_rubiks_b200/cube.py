@@ -9,7 +9,8 @@ tensors and then keeps the data on the device (tensor in -> tensor out), which i
 and the search frontier use it.  There is no CPU path: all arithmetic runs in the sm_100a kernels.
 
 Additions with no reference analogue (derivable from the reference API): `expand12`,
-`scramble_batch`, `sequence_scrambler_from`.
+`scramble_batch`, `scramble_seeded` / `seeded_actions` (random draw made on the device), `pack_actions` /
+`scramble_batch_packed` (two moves per byte over PCIe), `sequence_scrambler_from`.
 """
 from __future__ import annotations
 
@@ -315,6 +316,67 @@ def scramble_batch(actions, start=None):
 	out = torch.empty(n, *shape(), dtype=torch.int8, device=a.device)
 	N.check(N.lib.rb_scramble(_rep(), N.ptr(a), depth, 1, N.ptr(st), N.ptr(out), n, depth, N.stream_handle()))
 	return _out(out, was_np)
+
+
+def scramble_seeded(n: int, depth: int, seed: int, first_cube: int = 0, start=None, host_out: bool = False):
+	"""`cube.scramble(depth)` for n cubes with the random draw made on the device: cube i takes `depth` moves, each uniform
+	over the 12 actions, from subsequence `first_cube + i` of the Philox4x32-10 stream keyed by `seed` (the result for a cube
+	does not depend on how cubes are split over calls or GPUs).  Returns the (n, *shape()) final states as a CUDA tensor, or
+	written straight into a numpy array through the host-buffer C-ABI call when `host_out` (nothing but the seed is sent to the
+	device).  `seeded_actions` returns the moves that were applied."""
+	n, depth, seed, first_cube = int(n), int(depth), int(seed) & (2 ** 64 - 1), int(first_cube) & (2 ** 64 - 1)
+	if host_out:
+		if start is not None:
+			raise ValueError("host_out does not take start states")
+		N.require_cuda()
+		out = np.empty((n, *shape()), dtype=np.int8)
+		N.check(N.lib.rbh_scramble_seeded(_rep(), seed, first_cube, out.ctypes.data, n, depth))
+		return out
+	st = None
+	if start is not None:
+		st, _, _ = _states_in(start)
+		if st.shape[0] != n:
+			raise IndexError(f"expected {n} start states, got {st.shape[0]}")
+	out = torch.empty(n, *shape(), dtype=torch.int8, device=_dev())
+	N.check(N.lib.rb_scramble_seeded(_rep(), seed, first_cube, N.ptr(st), N.ptr(out), n, depth, N.stream_handle()))
+	return out
+
+
+def seeded_actions(n: int, depth: int, seed: int, first_cube: int = 0) -> torch.Tensor:
+	"""The action indices `scramble_seeded` applies: uint8 (n, depth) CUDA tensor."""
+	a = torch.empty(int(n), int(depth), dtype=torch.uint8, device=_dev())
+	N.check(N.lib.rb_seeded_actions(int(seed) & (2 ** 64 - 1), int(first_cube) & (2 ** 64 - 1), N.ptr(a), int(n), int(depth), N.stream_handle()))
+	return a
+
+
+def pack_actions(actions: np.ndarray) -> np.ndarray:
+	"""(n, depth) action indices -> (n, (depth + 1) // 2) packed bytes, two moves each: p = a[2k] + 13 * a[2k+1] (12 = no second
+	move) -- the format of `scramble_batch_packed` / `rbh_scramble_packed` (half the bytes over PCIe)."""
+	a = np.asarray(actions)
+	if a.ndim != 2:
+		raise IndexError("actions must be (n, depth)")
+	if a.size and (a.min() < 0 or a.max() > 11):
+		raise IndexError("action index out of range")
+	a = a.astype(np.uint8)
+	if a.shape[1] % 2:
+		a = np.concatenate([a, np.full((len(a), 1), 12, np.uint8)], axis=1)
+	return np.ascontiguousarray(a[:, 0::2] + 13 * a[:, 1::2])
+
+
+def scramble_batch_packed(packed: np.ndarray, depth: int) -> np.ndarray:
+	"""`scramble_batch` on packed host actions (see `pack_actions`); numpy in, numpy out through the host-buffer C-ABI call."""
+	N.require_cuda()
+	p = np.ascontiguousarray(packed, dtype=np.uint8)
+	if p.ndim != 2 or p.shape[1] != (depth + 1) // 2:
+		raise IndexError(f"packed actions must be (n, {(depth + 1) // 2})")
+	if p.size:
+		hi, lo = p // 13, p % 13
+		ok = (lo < 12).all() and (hi[:, :depth // 2] < 12).all() and (hi <= 12).all() and (depth % 2 == 0 or (hi[:, -1] == 12).all())
+		if not ok:
+			raise IndexError("packed action byte out of range")
+	out = np.empty((len(p), *shape()), dtype=np.int8)
+	N.check(N.lib.rbh_scramble_packed(_rep(), p.ctypes.data, out.ctypes.data, len(p), int(depth)))
+	return out
 
 
 def scramble(depth: int, force_not_solved=False):

@@ -308,3 +308,19 @@ def test_mcts_full_trace(golden, tag, c, graph, max_states):
 	assert (m.states[1:L + 1] == g[f"mcts{tag}_states"]).all()
 	assert (m.neighbors[:L + 1] == g[f"mcts{tag}_neighbors"]).all() and (m.leaves[:L + 1] == g[f"mcts{tag}_leaves"]).all()
 	assert (m.N[:L + 1] == g[f"mcts{tag}_N"]).all() and (m.W[1:L + 1] == g[f"mcts{tag}_W"]).all() and (m.V[1:L + 1] == g[f"mcts{tag}_V"]).all()
+
+
+# ---- device-seeded stream: the generator restated in the oracle is Philox4x32-10 ---------------------------------------
+def test_philox4x32_10_known_answers():
+	"""Random123 kat_vectors (philox4x32 10): counter, key -> output."""
+	kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+		   ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+		   ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+	for ctr, key, want in kat:
+		assert O.philox4x32_10(np.array([ctr], dtype=np.uint32), key)[0].tolist() == list(want)
+	a = O.seeded_actions(1234, 5, 64, 100)
+	assert a.shape == (64, 100) and a.max() == 11 and a.min() == 0
+	assert (O.seeded_actions(1234, 5, 64, 37) == a[:, :37]).all()               # prefix property
+	assert (O.seeded_actions(1234, 25, 10, 100) == a[20:30]).all()              # cube id = subsequence
+	for depth in (100, 37):
+		assert (O.unpack_actions(O.pack_actions(a[:, :depth]), depth) == a[:, :depth]).all()
