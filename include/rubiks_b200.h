@@ -169,9 +169,12 @@ int rb_adi_loss_weights(float* out, int32_t games, int32_t depth, double alpha, 
 /* Open-addressing hash set keyed on the packed state, 128 bit: 20x24 -> 20 cubies x 5 bit = 100 bit;
  * 6x8x6 -> the 8 sticker colours of each face as a base-6 number (6^8 < 2^21), 6 x 21 = 126 bit, injective on
  * valid one-hot states (the only ones a cube can reach).
- * The table lives in caller-owned device memory of rb_hashset_bytes(capacity) bytes; capacity must be a
- * power of two.  The set maps state -> index (int32, 1-based in insertion order like the reference's
- * `indices` dict; 0 = absent). */
+ * The table lives in caller-owned device memory of rb_hashset_bytes(capacity) bytes (32 per slot), 32-byte aligned; capacity
+ * must be a power of two <= 2^30 (RB_ERR_CAPACITY above that).  The set maps state -> index (int32, 1-based in insertion order
+ * like the reference's `indices` dict; 0 = absent).
+ * Overflow: a batch that finds the table full cannot report it through the return value (nothing synchronises); it sets
+ * *count_dev (and *n_new_dev) to -1, which every later batch on that counter preserves, and gives the dropped items index -1.
+ * Keep the load factor <= 1/2 (the Python mirror grows the table with rb_hashset_rehash before a batch could exceed it). */
 int64_t rb_hashset_bytes(int64_t capacity);
 int rb_hashset_clear(void* table, int64_t capacity, rb_stream_t stream);
 /* Growth: clears `dst` (dst_capacity >= src_capacity) and re-inserts every (state key, index) pair of `src`. */

@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kThreads) k_probe(View v) {
 	const rbf::Table t = rbf::table_of(v.table, v.capacity);
 	const int64_t slot = rbf::find_or_claim(t, k);
 	v.slot[(int64_t)s * v.P() + i] = (int32_t)slot;
-	if (slot >= 0) atomicMin(t.firstpos + slot, (uint32_t)i);
+	if (slot >= 0) atomicMin(&t.firstpos(slot), (uint32_t)i);
 }
 
 __global__ void __launch_bounds__(kThreads) k_flag(View v) {
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kThreads) k_flag(View v) {
 	if (i < v.n_sel[s] * 12) {
 		const int32_t slot = v.slot[(int64_t)s * v.P() + i];
 		bool seen = false, first = false;
-		if (slot >= 0) { seen = t.vals[slot] != 0; first = t.firstpos[slot] == (uint32_t)i; }
+		if (slot >= 0) { seen = t.val(slot) != 0; first = t.firstpos(slot) == (uint32_t)i; }
 		is_new = first && !seen;
 		v.flags[(int64_t)s * v.P() + i] = (uint8_t)((is_new ? 1 : 0) | ((first && seen) ? 2 : 0));
 	}
@@ -269,7 +269,7 @@ k_assign(View v, int8_t* __restrict__ new_states, int32_t* __restrict__ new_sear
 	const int k = prefix + r;
 	const int idx = v.count[s] + k + 1;
 	const rbf::Table t = rbf::table_of(v.table, v.capacity);
-	t.vals[v.slot[(int64_t)s * v.P() + i]] = idx;
+	t.val(v.slot[(int64_t)s * v.P() + i]) = idx;
 	uint32_t w[5]; int parent;
 	child_words(v, s, i, s_lut, w, parent);
 	const int64_t row = (int64_t)s * v.M + idx;
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(kThreads) k_relax_eval(View v, int pass) {
 	uint8_t f = v.flags[it] & 3;
 	if (f & 2) {
 		const rbf::Table t = rbf::table_of(v.table, v.capacity);
-		const int st = t.vals[v.slot[it]], par = v.sel[(int64_t)s * v.N + i / 12];
+		const int st = t.val(v.slot[it]), par = v.sel[(int64_t)s * v.N + i / 12];
 		const double gs = v.G[(int64_t)s * v.M + st], gp = v.G[(int64_t)s * v.M + par];
 		const double val = pass == 0 ? gp + 1.0 : gs + 1.0;     // new way to the state / shortcut to the parent
 		if (pass == 0 ? val < gs : val < gp) { f |= 4; v.tmp[it] = val; }
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(kThreads) k_relax_new_ways(View v) {
 	const int64_t it = (int64_t)s * v.P() + i;
 	if (!(v.flags[it] & 4)) return;
 	const rbf::Table t = rbf::table_of(v.table, v.capacity);
-	const int64_t row = (int64_t)s * v.M + t.vals[v.slot[it]];
+	const int64_t row = (int64_t)s * v.M + t.val(v.slot[it]);
 	v.G[row] = v.tmp[it];
 	v.parent_actions[row] = (uint8_t)(i % 12);
 	v.parents[row] = v.sel[(int64_t)s * v.N + i / 12];
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(kThreads) k_relax_shortcuts(View v) {
 		if (v.flags[it] & 4) {
 			v.G[row] = v.tmp[it];
 			v.parent_actions[row] = (uint8_t)(a ^ 1);               // rev_action
-			v.parents[row] = t.vals[v.slot[it]];
+			v.parents[row] = t.val(v.slot[it]);
 		}
 	}
 }
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(kThreads) k_finish(View v) {
 	const int s = blockIdx.y, i = blockIdx.x * kThreads + threadIdx.x;
 	if (i < v.n_sel[s] * 12) {
 		const int32_t slot = v.slot[(int64_t)s * v.P() + i];
-		if (slot >= 0) rbf::table_of(v.table, v.capacity).firstpos[slot] = 0xffffffffu;
+		if (slot >= 0) rbf::table_of(v.table, v.capacity).firstpos(slot) = 0xffffffffu;
 	}
 	if (i == 0) v.count[s] += v.n_sel[s] ? v.n_new[s] : 0;
 }
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(kThreads) k_init(View v, const int8_t* __restr
 	k.hi |= (unsigned long long)s << 40;
 	const rbf::Table t = rbf::table_of(v.table, v.capacity);
 	const int64_t slot = rbf::find_or_claim(t, k);
-	if (slot >= 0) t.vals[slot] = 1;
+	if (slot >= 0) t.val(slot) = 1;
 	const uint32_t* sv = reinterpret_cast<const uint32_t*>(g_solved2024);
 	const bool solved = (w[0] == sv[0]) & (w[1] == sv[1]) & (w[2] == sv[2]) & (w[3] == sv[3]) & (w[4] == sv[4]);
 	const int64_t row = (int64_t)s * v.M + 1;

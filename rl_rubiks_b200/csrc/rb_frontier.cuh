@@ -4,23 +4,33 @@
 // Replaces the Python dict keyed on `state.tostring()` of BFS / AStar / MCTS
 // (reference: librubiks/solving/agents.py:103-121, 286-306, 517-526, 605-609).
 //
-// Table layout in caller-owned HBM (capacity C slots, C a power of two, 24 B per slot):
-//   keys     [C] 2 x u64   packed state; all-ones = empty.  Claimed with one 128-bit atom.cas.
-//   vals     [C] i32       1-based index of the state (insertion order); 0 = inserted in the running batch
-//   firstpos [C] u32       minimum batch position that touched the slot in the running batch (0xffffffff idle)
-// (Three parallel arrays on purpose: `vals` and `firstpos` of a 2^24-slot table are 64 MB each and live in the 126 MB L2
-// across the five phases of a batch.  One 32-byte struct per slot was measured 12-20 % slower -- BFS depth 7: 2.75 vs
-// 2.45 ms, 2^22 inserts: 0.88 vs 0.73 ms -- because every phase then misses to DRAM.)
+// Table layout in caller-owned HBM: capacity C slots (C a power of two <= 2^30), one 32-byte slot per state
+//   key      2 x u64   packed state; all-ones = empty.  Claimed with one 128-bit atom.cas.
+//   val      i32       1-based index of the state (insertion order); 0 = claimed in the running batch, not numbered yet
+//   firstpos u32       minimum batch position that touched the slot in the running batch (0xffffffff idle)
+//   (8 bytes spare)
+// A slot is one 32-byte sector, so every phase of a batch costs ONE random DRAM burst per item.  (Round 1 kept three parallel
+// arrays -- keys / vals / firstpos -- and five phases; ncu showed 140 B of DRAM reads per item and phase, two 64-byte bursts,
+// 5.3 GB per depth-7 BFS closure against 0.7 GB algorithmic: profiles/r1k_frontier_bfs7_launches.txt.)
 // Keys: 20x24 -> 20 cubies x 5 bit = 100 bit (lo = cubies 0-11, hi = cubies 12-19).
 //       6x8x6 -> per face the 8 sticker colours as a base-6 number (< 6^8 < 2^21), faces 0-2 in lo, 3-5 in hi;
 //       injective on valid (one-hot) states.
 //
-// Batch insert = 5 small launches, no host synchronisation:
-//   probe  : every item finds or claims its slot, atomicMin(firstpos[slot], position)
-//   flag   : seen = vals[slot] != 0; first = firstpos[slot] == position; per-block count of new = first & !seen
-//   scan   : exclusive scan of the block counts (one block)
-//   assign : new items get index count + rank + 1 in batch order (vals[slot] = index) and are compacted
-//   finish : index[i] = vals[slot_i]; firstpos reset; count += number of new states
+// Batch insert = 2 launches (3 when the caller wants every item's index), no host synchronisation:
+//   probe   : every item finds or claims its slot; seen = val != 0 (states numbered by earlier batches); items not seen
+//             (and seen ones too when the caller asks for the `first` flags) do old = atomicMin(firstpos, position) and, when
+//             the slot was already in the race, mark the LOSER max(old, position) in a byte-per-item scratch array: at the end
+//             of the pass exactly the minimum position of every slot is unmarked -- the first occurrence is known without
+//             reading the table again.  The slot number and the seen bit go to a scratch word per item; seen items already
+//             know their index
+//   resolve : first = not marked; new = first & !seen; ONE pass numbers the new items in batch order -- a decoupled
+//             look-back scan over the blocks' counts (each block publishes its count, then its inclusive prefix; blocks take
+//             their number from a ticket so that every predecessor is resident or done) -- stores val = count + rank + 1 and
+//             re-arms firstpos (one 8-byte store into the slot, no table read in this pass), compacts the new items (state,
+//             parent, action, solved) and, in the last block, count += total
+//   index   : (optional) items that were not seen read their state's index back
+// A full table (a probe that wraps around) sets an error word: count (and n_new) become -1 and stay so -- the caller sees
+// RB_ERR_CAPACITY semantics without a host sync inside the call (the Python mirror raises on the next read of the size).
 #pragma once
 #include "rb_common.cuh"
 
@@ -28,21 +38,29 @@ namespace rbf {
 
 constexpr int kThreads = 256;
 constexpr unsigned long long kEmpty = ~0ull;
+constexpr int64_t kMaxCapacity = int64_t(1) << 30;          // slot numbers travel in 31 bits (+ the seen bit)
+constexpr uint32_t kNoSlot = 0xffffffffu;                   // scratch word of an item dropped by a full table
 
 struct Key { unsigned long long lo, hi; };
 
+struct __align__(32) Slot {
+	unsigned long long lo, hi;
+	int32_t val;
+	uint32_t firstpos;
+	unsigned long long spare;
+};
+
 struct Table {
-	ulonglong2* keys;
-	int32_t* vals;
-	uint32_t* firstpos;
+	Slot* slots;
 	uint64_t mask;
+	__device__ __forceinline__ ulonglong2* key(int64_t s) const { return reinterpret_cast<ulonglong2*>(slots + s); }
+	__device__ __forceinline__ int32_t& val(int64_t s) const { return slots[s].val; }
+	__device__ __forceinline__ uint32_t& firstpos(int64_t s) const { return slots[s].firstpos; }
 };
 
 __host__ __device__ inline Table table_of(void* base, int64_t capacity) {
 	Table t;
-	t.keys = reinterpret_cast<ulonglong2*>(base);
-	t.vals = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(base) + capacity * 16);
-	t.firstpos = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(base) + capacity * 20);
+	t.slots = reinterpret_cast<Slot*>(base);
 	t.mask = (uint64_t)capacity - 1;
 	return t;
 }
@@ -90,15 +108,25 @@ __device__ __forceinline__ ulonglong2 ld128_volatile(const ulonglong2* addr) {
 	asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(addr) : "memory");
 	return v;
 }
+__device__ __forceinline__ int32_t ld32_volatile(const int32_t* addr) {
+	int32_t v;
+	asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+	return v;
+}
 
-// Find the slot holding `k`, claiming an empty one if absent.  Returns -1 when the table is full.
-__device__ __forceinline__ int64_t find_or_claim(const Table& t, Key k) {
+// Find the slot holding `k`, claiming an empty one if absent.  Returns -1 when the table is full; *claimed = this call put the
+// key there (the slot is fresh: val 0, firstpos idle).
+__device__ __forceinline__ int64_t find_or_claim(const Table& t, Key k, bool* claimed = nullptr) {
 	uint64_t s = hash_key(k) & t.mask;
+	if (claimed) *claimed = false;
 	for (uint64_t probes = 0; probes <= t.mask; ++probes, s = (s + 1) & t.mask) {
-		ulonglong2 cur = ld128_volatile(t.keys + s);
+		ulonglong2 cur = ld128_volatile(t.key(s));
 		if (cur.x == kEmpty && cur.y == kEmpty) {
-			cur = cas128(t.keys + s, make_ulonglong2(kEmpty, kEmpty), make_ulonglong2(k.lo, k.hi));
-			if (cur.x == kEmpty && cur.y == kEmpty) return (int64_t)s;
+			cur = cas128(t.key(s), make_ulonglong2(kEmpty, kEmpty), make_ulonglong2(k.lo, k.hi));
+			if (cur.x == kEmpty && cur.y == kEmpty) {
+				if (claimed) *claimed = true;
+				return (int64_t)s;
+			}
 		}
 		if (cur.x == k.lo && cur.y == k.hi) return (int64_t)s;
 	}
@@ -108,7 +136,7 @@ __device__ __forceinline__ int64_t find_or_claim(const Table& t, Key k) {
 __device__ __forceinline__ int64_t find_only(const Table& t, Key k) {
 	uint64_t s = hash_key(k) & t.mask;
 	for (uint64_t probes = 0; probes <= t.mask; ++probes, s = (s + 1) & t.mask) {
-		const ulonglong2 cur = t.keys[s];
+		const ulonglong2 cur = *t.key(s);
 		if (cur.x == k.lo && cur.y == k.hi) return (int64_t)s;
 		if (cur.x == kEmpty && cur.y == kEmpty) return -1;
 	}
@@ -116,22 +144,19 @@ __device__ __forceinline__ int64_t find_only(const Table& t, Key k) {
 }
 
 __global__ void __launch_bounds__(kThreads) k_clear(void* base, int64_t capacity) {
-	const Table t = table_of(base, capacity);
-	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < capacity; i += (int64_t)gridDim.x * blockDim.x) {
-		t.keys[i] = make_ulonglong2(kEmpty, kEmpty);
-		t.vals[i] = 0;
-		t.firstpos[i] = 0xffffffffu;
-	}
+	uint4* p = reinterpret_cast<uint4*>(base);                    // slot = {key all-ones} {val 0, firstpos idle, spare 0}
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * capacity; i += (int64_t)gridDim.x * blockDim.x)
+		p[i] = (i & 1) ? make_uint4(0u, 0xffffffffu, 0u, 0u) : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
 }
 
 // Move every (key, index) pair of `src` into the (cleared, larger) table `dst`.
 __global__ void __launch_bounds__(kThreads) k_rehash(void* src_base, int64_t src_cap, void* dst_base, int64_t dst_cap) {
 	const Table s = table_of(src_base, src_cap), d = table_of(dst_base, dst_cap);
 	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < src_cap; i += (int64_t)gridDim.x * blockDim.x) {
-		const ulonglong2 k = s.keys[i];
+		const ulonglong2 k = *s.key(i);
 		if (k.x == kEmpty && k.y == kEmpty) continue;
 		const int64_t slot = find_or_claim(d, Key{k.x, k.y});
-		if (slot >= 0) d.vals[slot] = s.vals[i];
+		if (slot >= 0) d.val(slot) = s.val(i);
 	}
 }
 
@@ -152,56 +177,84 @@ struct FromArray2024 {           // item i = states[i]
 struct FromParent2024 {          // item i = action (i % 12) applied to frontier[i / 12]
 	const int8_t* frontier;
 	__device__ __forceinline__ void load(int64_t i, const uint8_t* s_lut, uint32_t (&w)[5]) const {
-		FromArray2024{frontier}.load(i / 12, s_lut, w);
-		rb_move2024(s_lut, (uint32_t)(i % 12), w);
+		const uint32_t u = (uint32_t)i, par = u / 12u;           // item numbers fit 31 bits (checked by the entry points): no 64-bit division
+		FromArray2024{frontier}.load(par, s_lut, w);
+		rb_move2024(s_lut, u - 12u * par, w);
 	}
 };
 
 // scratch layout for a batch of n items
 struct Scratch {
-	int32_t* slot;        // [n]   slot of every item (-1 = table full)
-	int32_t* block_new;   // [nb + 1] per-block count of new items, then exclusive offsets; [nb] = total
-	ulonglong2* keys;     // [n]   6x8x6 only: packed keys
+	uint32_t* word;               // [n]  slot | seen << 31 of every item; kNoSlot = dropped by a full table
+	uint8_t* lost;                // [n]  1 = another item of this batch with a smaller position has the same state
+	unsigned long long* status;   // [nb] look-back state of the resolve pass: flag << 32 | count (flag 1 = block count, 2 = inclusive prefix)
+	uint32_t* ctl;                // [4]  ticket, error word, 2 spare (lost, status and ctl are zeroed by ONE memset per batch)
+	ulonglong2* keys;             // [n]  6x8x6 only: packed keys
 	int64_t nb;
 };
 __host__ __device__ inline int64_t n_blocks(int64_t n) { return (n + kThreads - 1) / kThreads; }
+__host__ __device__ inline int64_t up16(int64_t x) { return (x + 15) / 16 * 16; }
 __host__ __device__ inline Scratch scratch_of(void* base, int64_t n) {
 	Scratch s;
 	s.nb = n_blocks(n);
-	s.slot = reinterpret_cast<int32_t*>(base);
-	s.block_new = s.slot + ((n + 3) / 4) * 4;
-	s.keys = reinterpret_cast<ulonglong2*>(s.block_new + ((s.nb + 1 + 3) / 4) * 4);
+	uint8_t* p = reinterpret_cast<uint8_t*>(base);
+	s.word = reinterpret_cast<uint32_t*>(p); p += up16(n * 4);
+	s.lost = p; p += up16(n);
+	s.status = reinterpret_cast<unsigned long long*>(p); p += up16(s.nb * 8);
+	s.ctl = reinterpret_cast<uint32_t*>(p); p += 16;
+	s.keys = reinterpret_cast<ulonglong2*>(p);
 	return s;
 }
-inline int64_t scratch_bytes(int64_t n, bool with_keys) {
-	return ((n + 3) / 4) * 16 + ((n_blocks(n) + 1 + 3) / 4) * 16 + (with_keys ? n * 16 : 0) + 16;
+inline int64_t scratch_bytes(int64_t n, bool with_keys) { return up16(n * 4) + up16(n) + up16(n_blocks(n) * 8) + 16 + (with_keys ? n * 16 : 0) + 16; }
+inline int64_t control_bytes(int64_t n) { return up16(n) + up16(n_blocks(n) * 8) + 16; }       // lost + status + ctl: zeroed before a batch (from .lost)
+
+// ---- probe ------------------------------------------------------------------------------------------------------------------
+// One item: find or claim the slot, read whether an earlier batch numbered the state, join the race for "first occurrence in
+// this batch" and leave slot | seen << 31 in the scratch word.
+__device__ __forceinline__ void probe_item(const Table& t, Key k, int64_t i, bool need_first, uint32_t* __restrict__ word, uint8_t* lost,
+                                           uint32_t* __restrict__ ctl, uint8_t* __restrict__ seen, int32_t* __restrict__ index) {
+	bool claimed;
+	const int64_t s = find_or_claim(t, k, &claimed);
+	if (s < 0) {
+		word[i] = kNoSlot;
+		atomicOr(ctl + 1, 1u);
+		if (seen) seen[i] = 0;
+		if (index) index[i] = -1;
+		return;
+	}
+	// numbered by an earlier batch?  (vals of this batch are written by resolve; a slot this item claimed is fresh: no read)
+	const int32_t v = claimed ? 0 : ld32_volatile(&t.val(s));
+	const bool sn = v != 0;
+	if (!sn || need_first) {
+		const uint32_t old = atomicMin(&t.firstpos(s), (uint32_t)i);      // the sector was just read / claimed: an L2 hit
+		if (old != 0xffffffffu) lost[old > (uint32_t)i ? old : (uint32_t)i] = 1;
+	}
+	word[i] = (uint32_t)s | (sn ? 0x80000000u : 0u);
+	if (seen) seen[i] = sn;
+	if (index && sn) index[i] = v;
 }
 
 template <class Provider>
 __global__ void __launch_bounds__(kThreads)
-k_probe2024(Provider prov, void* base, int64_t capacity, int64_t n, int32_t* __restrict__ slot) {
+k_probe2024(Provider prov, void* base, int64_t capacity, int64_t n, int need_first, uint32_t* __restrict__ word, uint8_t* lost,
+            uint32_t* __restrict__ ctl, uint8_t* __restrict__ seen, int32_t* __restrict__ index) {
 	__shared__ __align__(16) uint8_t s_lut[RB_LUT_BYTES];
 	rb_stage_lut2024(s_lut);
 	__syncthreads();
-	const Table t = table_of(base, capacity);
 	const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
 	if (i >= n) return;
 	uint32_t w[5];
 	prov.load(i, s_lut, w);
-	const int64_t s = find_or_claim(t, pack2024(w));
-	slot[i] = (int32_t)s;
-	if (s >= 0) atomicMin(t.firstpos + s, (uint32_t)i);
+	probe_item(table_of(base, capacity), pack2024(w), i, need_first != 0, word, lost, ctl, seen, index);
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_probe_keys(const ulonglong2* __restrict__ keys, void* base, int64_t capacity, int64_t n, int32_t* __restrict__ slot) {
-	const Table t = table_of(base, capacity);
+k_probe_keys(const ulonglong2* __restrict__ keys, void* base, int64_t capacity, int64_t n, int need_first, uint32_t* __restrict__ word,
+             uint8_t* lost, uint32_t* __restrict__ ctl, uint8_t* __restrict__ seen, int32_t* __restrict__ index) {
 	const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
 	if (i >= n) return;
 	const ulonglong2 k = keys[i];
-	const int64_t s = find_or_claim(t, Key{k.x, k.y});
-	slot[i] = (int32_t)s;
-	if (s >= 0) atomicMin(t.firstpos + s, (uint32_t)i);
+	probe_item(table_of(base, capacity), Key{k.x, k.y}, i, need_first != 0, word, lost, ctl, seen, index);
 }
 
 // 6x8x6 packing: warp per state; lane = one of 48 stickers (two rounds), colour = index of the set byte.
@@ -235,108 +288,122 @@ k_pack686(const int8_t* __restrict__ states, int64_t n, ulonglong2* __restrict__
 	if (lane == 0) keys[warp] = make_ulonglong2(f0 | (f1 << 21) | (f2 << 42), f3 | (f4 << 21) | (f5 << 42));
 }
 
-// flags + per-block count of new items
-__global__ void __launch_bounds__(kThreads)
-k_flag(void* base, int64_t capacity, int64_t n, const int32_t* __restrict__ slot, uint8_t* __restrict__ seen,
-       uint8_t* __restrict__ first, int32_t* __restrict__ block_new) {
-	const Table t = table_of(base, capacity);
-	const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-	bool is_new = false;
-	if (i < n) {
-		const int32_t s = slot[i];
-		bool sn = false, fs = false;
-		if (s >= 0) {
-			sn = t.vals[s] != 0;
-			fs = t.firstpos[s] == (uint32_t)i;
-		}
-		if (seen) seen[i] = sn;
-		if (first) first[i] = fs;
-		is_new = fs && !sn;
-	}
-	const int c = __syncthreads_count(is_new);
-	if (threadIdx.x == 0) block_new[blockIdx.x] = c;
+// ---- resolve ----------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
+	unsigned long long v;
+	asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v) {
+	asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// exclusive scan of block counts in place; block_new[nb] = total.  One block.
-__global__ void __launch_bounds__(1024) k_scan(int32_t* __restrict__ block_new, int64_t nb) {
-	__shared__ int32_t s_warp[32];
-	__shared__ int32_t s_carry;
-	if (threadIdx.x == 0) s_carry = 0;
-	__syncthreads();
-	for (int64_t base = 0; base < nb; base += 1024) {
-		const int64_t i = base + threadIdx.x;
-		const int32_t x = i < nb ? block_new[i] : 0;
-		int32_t v = x;
+// Exclusive prefix of this block's count over all earlier blocks (decoupled look-back, Merrill & Garland): warp 0 publishes
+// the block's count, walks back over the predecessors' status words 32 at a time until it meets an inclusive prefix, then
+// publishes its own inclusive prefix.  `b` is the block's ticket, so every predecessor is running or done.
+__device__ __forceinline__ int32_t lookback(unsigned long long* status, int32_t b, int32_t agg) {
+	const int lane = threadIdx.x & 31;
+	if (lane == 0) st_status(status + b, ((unsigned long long)(b == 0 ? 2 : 1) << 32) | (uint32_t)agg);
+	int32_t excl = 0;
+	for (int32_t j = b - 1; j >= 0;) {
+		const int32_t idx = j - lane;
+		const unsigned long long v = idx >= 0 ? ld_status(status + idx) : (2ull << 32);
+		const uint32_t flag = (uint32_t)(v >> 32);
+		const unsigned ready = __ballot_sync(0xffffffffu, flag != 0), incl = __ballot_sync(0xffffffffu, flag == 2);
+		const int stop = incl ? __ffs(incl) - 1 : 31;                       // nearest predecessor that already has its inclusive prefix
+		const unsigned need = stop == 31 ? 0xffffffffu : ((2u << stop) - 1u);
+		if ((ready & need) != need) continue;                               // some predecessor in the window has not published yet
+		int32_t c = lane <= stop ? (int32_t)(uint32_t)v : 0;
 #pragma unroll
-		for (int o = 1; o < 32; o <<= 1) {
-			const int32_t y = __shfl_up_sync(0xffffffffu, v, o);
-			if ((threadIdx.x & 31) >= o) v += y;
-		}
-		if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = v;
-		__syncthreads();
-		if (threadIdx.x < 32) {
-			int32_t wv = s_warp[threadIdx.x];
-#pragma unroll
-			for (int o = 1; o < 32; o <<= 1) {
-				const int32_t y = __shfl_up_sync(0xffffffffu, wv, o);
-				if (threadIdx.x >= o) wv += y;
-			}
-			s_warp[threadIdx.x] = wv;
-		}
-		__syncthreads();
-		const int32_t carry = s_carry;
-		const int32_t incl = v + (threadIdx.x >= 32 ? s_warp[(threadIdx.x >> 5) - 1] : 0);
-		if (i < nb) block_new[i] = carry + incl - x;
-		__syncthreads();
-		if (threadIdx.x == 1023) s_carry = carry + incl;
-		__syncthreads();
+		for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+		excl += c;
+		if (incl) break;
+		j -= 32;
 	}
-	if (threadIdx.x == 0) block_new[nb] = s_carry;
+	if (lane == 0 && b > 0) st_status(status + b, (2ull << 32) | (uint32_t)(excl + agg));
+	return excl;
 }
 
-// Rank of a new item inside its block (batch order), via ballot + warp prefix.
-__device__ __forceinline__ int block_rank(bool flag, int32_t* s_warp) {
+// Rank of a new item inside its block (batch order), via ballot + warp prefix; *total = the block's count.
+__device__ __forceinline__ int block_rank(bool flag, int32_t* s_warp, int32_t* total = nullptr) {
 	const unsigned m = __ballot_sync(0xffffffffu, flag);
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	if (lane == 0) s_warp[wid] = __popc(m);
 	__syncthreads();
-	int off = 0;
-	for (int k = 0; k < wid; ++k) off += s_warp[k];
+	int off = 0, all = 0;
+#pragma unroll
+	for (int k = 0; k < kThreads / 32; ++k) {
+		const int c = s_warp[k];
+		off += k < wid ? c : 0;
+		all += c;
+	}
+	if (total) *total = all;
 	return off + __popc(m & ((1u << lane) - 1u));
 }
 
-// assign indices to new items (batch order) and compact them.
-//   2024 provider given: writes next_frontier (state), parent, action, solved for each new item at its rank.
+// first / new flags, numbering of the new items in batch order, compaction -- one pass.
+//   kFrontier: the 2024 provider regenerates the item's state; new item k gets next_frontier / parent / action / solved row k.
+//   otherwise: new_items[k] = item number (6x8x6 frontier: gathered afterwards) or nothing (plain insert).
 template <class Provider, bool kFrontier>
 __global__ void __launch_bounds__(kThreads)
-k_assign2024(Provider prov, void* base, int64_t capacity, int64_t n, const int32_t* __restrict__ slot,
-             const int32_t* __restrict__ block_new, const int32_t* __restrict__ count, int8_t* __restrict__ next_frontier,
-             int32_t* __restrict__ parent, uint8_t* __restrict__ action, uint8_t* __restrict__ solved) {
+k_resolve(Provider prov, void* base, int64_t capacity, int64_t n, int need_first, const uint32_t* __restrict__ word,
+          const uint8_t* __restrict__ lost, unsigned long long* __restrict__ status, uint32_t* __restrict__ ctl, int32_t* __restrict__ count, int32_t* __restrict__ n_new,
+          uint8_t* __restrict__ first, int32_t* __restrict__ index, int32_t* __restrict__ new_items, int8_t* __restrict__ next_frontier,
+          int32_t* __restrict__ parent, uint8_t* __restrict__ action, uint8_t* __restrict__ solved) {
 	__shared__ __align__(16) uint8_t s_lut[RB_LUT_BYTES];
 	__shared__ int32_t s_warp[kThreads / 32];
+	__shared__ int32_t s_bid, s_excl, s_count;
 	if (kFrontier) rb_stage_lut2024(s_lut);
+	if (threadIdx.x == 0) s_bid = (int32_t)atomicAdd(ctl, 1u);
+	__syncthreads();
+	const int32_t b = s_bid;
 	const Table t = table_of(base, capacity);
-	const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-	int32_t s = -1;
-	bool is_new = false;
+	const int64_t i = (int64_t)b * kThreads + threadIdx.x;
+	uint32_t wd = kNoSlot;
+	bool fs = false, is_new = false;
 	if (i < n) {
-		s = slot[i];
-		if (s >= 0) is_new = t.vals[s] == 0 && t.firstpos[s] == (uint32_t)i;
+		wd = word[i];
+		if (wd != kNoSlot) {
+			const bool sn = (wd >> 31) != 0;
+			fs = (!sn || need_first) && !lost[i];                                  // no smaller position met this item's slot in the probe pass
+			is_new = fs && !sn;
+		}
+		if (first) first[i] = fs;
 	}
-	const int r = block_rank(is_new, s_warp);      // also orders the LUT staging before use
+	int32_t agg;
+	const int r = block_rank(is_new, s_warp, &agg);
+	if (threadIdx.x < 32) {
+		const int32_t c0 = *reinterpret_cast<volatile int32_t*>(count);          // read before this block publishes: the last block
+		const int32_t excl = lookback(status, b, agg);                            // rewrites count only after every block has read it
+		if (threadIdx.x == 0) {
+			s_excl = excl; s_count = c0;
+			if ((int64_t)b == (n + kThreads - 1) / kThreads - 1) {
+				const bool bad = c0 < 0 || *reinterpret_cast<volatile uint32_t*>(ctl + 1) != 0;
+				*count = bad ? -1 : c0 + excl + agg;
+				if (n_new) *n_new = bad ? -1 : excl + agg;
+			}
+		}
+	}
+	__syncthreads();
+	if (fs && !is_new) t.firstpos(wd & 0x7fffffffu) = 0xffffffffu;                // a seen slot that was raced for: re-armed by its winner
 	if (!is_new) return;
-	const int64_t k = (int64_t)block_new[blockIdx.x] + r;
-	t.vals[s] = *count + (int32_t)k + 1;
+	const int64_t k = (int64_t)s_excl + r;
+	const int32_t idx = s_count + (int32_t)k + 1;
+	// val and the re-armed firstpos in one 8-byte store: the only table access of this pass
+	*reinterpret_cast<uint2*>(&t.slots[wd & 0x7fffffffu].val) = make_uint2((uint32_t)idx, 0xffffffffu);
+	if (index) index[i] = idx;
+	if (new_items) new_items[k] = (int32_t)i;
 	if (kFrontier) {
 		uint32_t w[5];
 		prov.load(i, s_lut, w);
+		const uint32_t u = (uint32_t)i, par = u / 12u;
 		if (next_frontier) {
 			uint32_t* dst = reinterpret_cast<uint32_t*>(next_frontier + k * 20);     // 20 B records: 4-byte aligned
 #pragma unroll
 			for (int q = 0; q < 5; ++q) dst[q] = w[q];
 		}
-		if (parent) parent[k] = (int32_t)(i / 12);
-		if (action) action[k] = (uint8_t)(i % 12);
+		if (parent) parent[k] = (int32_t)par;
+		if (action) action[k] = (uint8_t)(u - 12u * par);
 		if (solved) {
 			const uint32_t* sv = reinterpret_cast<const uint32_t*>(g_solved2024);
 			solved[k] = (w[0] == sv[0]) & (w[1] == sv[1]) & (w[2] == sv[2]) & (w[3] == sv[3]) & (w[4] == sv[4]);
@@ -344,41 +411,20 @@ k_assign2024(Provider prov, void* base, int64_t capacity, int64_t n, const int32
 	}
 }
 
-// generic assign on precomputed slots (no state provider): only vals + optional compaction of item ids
-__global__ void __launch_bounds__(kThreads)
-k_assign_ids(void* base, int64_t capacity, int64_t n, const int32_t* __restrict__ slot, const int32_t* __restrict__ block_new,
-             const int32_t* __restrict__ count, int32_t* __restrict__ new_items) {
-	__shared__ int32_t s_warp[kThreads / 32];
-	const Table t = table_of(base, capacity);
-	const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-	int32_t s = -1;
-	bool is_new = false;
-	if (i < n) {
-		s = slot[i];
-		if (s >= 0) is_new = t.vals[s] == 0 && t.firstpos[s] == (uint32_t)i;
-	}
-	const int r = block_rank(is_new, s_warp);
-	if (!is_new) return;
-	const int64_t k = (int64_t)block_new[blockIdx.x] + r;
-	t.vals[s] = *count + (int32_t)k + 1;
-	if (new_items) new_items[k] = (int32_t)i;
-}
+struct NoProvider {
+	__device__ __forceinline__ void load(int64_t, const uint8_t*, uint32_t (&)[5]) const {}
+};
 
-// index[i] = vals[slot_i]; firstpos reset; count += total (after every block has read it: done by a second tiny launch)
+// index of the items that were claimed in this batch but are not its first occurrence (the others know theirs already)
 __global__ void __launch_bounds__(kThreads)
-k_finish(void* base, int64_t capacity, int64_t n, const int32_t* __restrict__ slot, int32_t* __restrict__ index) {
-	const Table t = table_of(base, capacity);
+k_index_rest(const void* base, int64_t capacity, int64_t n, const uint32_t* __restrict__ word, const uint8_t* __restrict__ first,
+             int32_t* __restrict__ index) {
+	const Table t = table_of(const_cast<void*>(base), capacity);
 	const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
 	if (i >= n) return;
-	const int32_t s = slot[i];
-	if (index) index[i] = s >= 0 ? t.vals[s] : -1;
-	if (s >= 0) t.firstpos[s] = 0xffffffffu;
-}
-
-__global__ void k_bump(int32_t* __restrict__ count, const int32_t* __restrict__ block_new, int64_t nb, int32_t* __restrict__ n_new) {
-	const int32_t total = block_new[nb];
-	if (n_new) *n_new = total;
-	*count += total;
+	const uint32_t wd = word[i];
+	if (wd == kNoSlot || (wd >> 31) || (first && first[i])) return;
+	index[i] = t.val(wd);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -389,7 +435,7 @@ k_lookup2024(const int8_t* __restrict__ states, const void* base, int64_t capaci
 	uint32_t w[5];
 	FromArray2024{states}.load(i, nullptr, w);
 	const int64_t s = find_only(t, pack2024(w));
-	index[i] = s >= 0 ? t.vals[s] : 0;
+	index[i] = s >= 0 ? t.val(s) : 0;
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -399,16 +445,16 @@ k_lookup_keys(const ulonglong2* __restrict__ keys, const void* base, int64_t cap
 	if (i >= n) return;
 	const ulonglong2 k = keys[i];
 	const int64_t s = find_only(t, Key{k.x, k.y});
-	index[i] = s >= 0 ? t.vals[s] : 0;
+	index[i] = s >= 0 ? t.val(s) : 0;
 }
 
 // 6x8x6 frontier compaction: gather the new children (ids in new_items) into next_frontier, with parent/action/solved.
 __global__ void __launch_bounds__(kThreads)
-k_gather686(const int8_t* __restrict__ children, const int32_t* __restrict__ new_items, const int32_t* __restrict__ block_new,
-            int64_t nb, int8_t* __restrict__ next_frontier, int32_t* __restrict__ parent, uint8_t* __restrict__ action,
+k_gather686(const int8_t* __restrict__ children, const int32_t* __restrict__ new_items, const int32_t* __restrict__ n_new_dev,
+            int8_t* __restrict__ next_frontier, int32_t* __restrict__ parent, uint8_t* __restrict__ action,
             uint8_t* __restrict__ solved) {
 	const int lane = threadIdx.x & 31;
-	const int64_t n_new = block_new[nb];
+	const int64_t n_new = *n_new_dev;
 	const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
 	const int64_t n_warps = (int64_t)gridDim.x * (kThreads / 32);
 	for (int64_t k = warp; k < n_new; k += n_warps) {

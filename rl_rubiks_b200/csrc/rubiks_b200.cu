@@ -345,20 +345,27 @@ int rb_adi_loss_weights(float* out, int32_t games, int32_t depth, double alpha, 
 }
 
 // ---- search frontier ----------------------------------------------------------------------------------------
-int64_t rb_hashset_bytes(int64_t capacity) { return capacity > 0 ? capacity * 24 : 0; }
+int64_t rb_hashset_bytes(int64_t capacity) { return capacity > 0 ? capacity * (int64_t)sizeof(rbf::Slot) : 0; }
 
 static bool pow2(int64_t x) { return x > 0 && (x & (x - 1)) == 0; }
+// a table the kernels can address: power-of-two capacity, slot numbers in 30 bits, 32-byte aligned slots
+#define RB_REQUIRE_TABLE(table, capacity)                                                                              \
+	do {                                                                                                               \
+		RB_REQUIRE((table) && pow2(capacity) && aligned((table), 32), "table must be 32-byte aligned with a power-of-two capacity"); \
+		if ((capacity) > rbf::kMaxCapacity) return rb_fail(RB_ERR_CAPACITY, "hash set capacity above 2^30 slots is not supported%s%s"); \
+	} while (0)
 
 int rb_hashset_clear(void* table, int64_t capacity, rb_stream_t stream) {
-	RB_REQUIRE(table && pow2(capacity) && aligned(table, 16), "table must be 16-byte aligned with a power-of-two capacity");
-	rbf::k_clear<<<rb_grid(capacity, rbf::kThreads * 4, 8), rbf::kThreads, 0, S(stream)>>>(table, capacity);
+	RB_REQUIRE_TABLE(table, capacity);
+	rbf::k_clear<<<rb_grid(2 * capacity, rbf::kThreads * 4, 8), rbf::kThreads, 0, S(stream)>>>(table, capacity);
 	RB_LAUNCHED("hashset_clear");
 	return RB_OK;
 }
 
 int rb_hashset_rehash(void* src, int64_t src_capacity, void* dst, int64_t dst_capacity, rb_stream_t stream) {
-	RB_REQUIRE(src && dst && pow2(src_capacity) && pow2(dst_capacity) && dst_capacity >= src_capacity && aligned(src, 16) && aligned(dst, 16),
-	           "bad tables");
+	RB_REQUIRE_TABLE(src, src_capacity);
+	RB_REQUIRE_TABLE(dst, dst_capacity);
+	RB_REQUIRE(dst_capacity >= src_capacity, "the new table must not be smaller");
 	int rc = rb_hashset_clear(dst, dst_capacity, stream);
 	if (rc != RB_OK) return rc;
 	rbf::k_rehash<<<rb_grid(src_capacity, rbf::kThreads * 4, 8), rbf::kThreads, 0, S(stream)>>>(src, src_capacity, dst, dst_capacity);
@@ -376,42 +383,35 @@ int64_t rb_frontier_scratch_bytes(int rep, int64_t n) {
 	return b;
 }
 
-// probe -> flag -> scan -> (assign by caller) shared by insert_unique and frontier_expand
-static int frontier_common_tail(void* table, int64_t capacity, int64_t items, const rbf::Scratch& sc, uint8_t* seen,
-                                uint8_t* first, cudaStream_t st) {
-	rbf::k_flag<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(table, capacity, items, sc.slot, seen, first, sc.block_new);
-	RB_LAUNCHED("frontier_flag");
-	rbf::k_scan<<<1, 1024, 0, st>>>(sc.block_new, sc.nb);
-	RB_LAUNCHED("frontier_scan");
-	return RB_OK;
-}
-
 int rb_hashset_insert_unique(int rep, void* table, int64_t capacity, const int8_t* states, int64_t n, int32_t* count_dev,
                              uint8_t* seen, uint8_t* first, int32_t* index, void* scratch, rb_stream_t stream) {
 	RB_REQUIRE(rep_ok(rep) && n >= 0 && n < (1ll << 31), "bad rep or size");
 	if (n == 0) return RB_OK;
-	RB_REQUIRE(table && pow2(capacity) && aligned(table, 16) && states && count_dev && scratch && aligned(scratch, 16), "bad table or pointers");
+	RB_REQUIRE_TABLE(table, capacity);
+	RB_REQUIRE(states && count_dev && scratch && aligned(scratch, 16), "bad pointers");
 	RB_INIT();
 	const rbf::Scratch sc = rbf::scratch_of(scratch, n);
 	cudaStream_t st = S(stream);
+	RB_CUDA(cudaMemsetAsync(sc.lost, 0, (size_t)rbf::control_bytes(n), st));
+	const int need_first = first != nullptr;
 	if (rep == RB_REP_2024) {
-		rbf::k_probe2024<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(rbf::FromArray2024{states}, table, capacity, n, sc.slot);
+		rbf::k_probe2024<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(rbf::FromArray2024{states}, table, capacity, n, need_first, sc.word, sc.lost, sc.ctl, seen, index);
 		RB_LAUNCHED("frontier_probe_2024");
 	} else {
 		RB_REQUIRE(aligned(states, 4), "6x8x6 states must be 4-byte aligned");
 		rbf::k_pack686<<<(unsigned)((n + 7) / 8), rbf::kThreads, 0, st>>>(states, n, sc.keys);
 		RB_LAUNCHED("frontier_pack_686");
-		rbf::k_probe_keys<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(sc.keys, table, capacity, n, sc.slot);
+		rbf::k_probe_keys<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(sc.keys, table, capacity, n, need_first, sc.word, sc.lost, sc.ctl, seen, index);
 		RB_LAUNCHED("frontier_probe_keys");
 	}
-	int rc = frontier_common_tail(table, capacity, n, sc, seen, first, st);
-	if (rc != RB_OK) return rc;
-	rbf::k_assign_ids<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(table, capacity, n, sc.slot, sc.block_new, count_dev, nullptr);
-	RB_LAUNCHED("frontier_assign");
-	rbf::k_finish<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(table, capacity, n, sc.slot, index);
-	RB_LAUNCHED("frontier_finish");
-	rbf::k_bump<<<1, 1, 0, st>>>(count_dev, sc.block_new, sc.nb, nullptr);
-	RB_LAUNCHED("frontier_bump");
+	rbf::k_resolve<rbf::NoProvider, false><<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(
+		rbf::NoProvider{}, table, capacity, n, need_first, sc.word, sc.lost, sc.status, sc.ctl, count_dev, nullptr, first, index, nullptr, nullptr, nullptr,
+		nullptr, nullptr);
+	RB_LAUNCHED("frontier_resolve");
+	if (index) {
+		rbf::k_index_rest<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(table, capacity, n, sc.word, first, index);
+		RB_LAUNCHED("frontier_index_rest");
+	}
 	return RB_OK;
 }
 
@@ -419,7 +419,8 @@ int rb_hashset_lookup(int rep, const void* table, int64_t capacity, const int8_t
                       void* scratch, rb_stream_t stream) {
 	RB_REQUIRE(rep_ok(rep) && n >= 0 && n < (1ll << 31), "bad rep or size");
 	if (n == 0) return RB_OK;
-	RB_REQUIRE(table && pow2(capacity) && states && index, "bad table or pointers");
+	RB_REQUIRE_TABLE(table, capacity);
+	RB_REQUIRE(states && index, "bad pointers");
 	RB_INIT();
 	cudaStream_t st = S(stream);
 	const unsigned nb = (unsigned)rbf::n_blocks(n);
@@ -445,43 +446,45 @@ int rb_frontier_expand(int rep, void* table, int64_t capacity, const int8_t* fro
 		if (n_new_dev) RB_CUDA(cudaMemsetAsync(n_new_dev, 0, sizeof(int32_t), S(stream)));
 		return RB_OK;
 	}
-	RB_REQUIRE(table && pow2(capacity) && aligned(table, 16) && frontier && count_dev && scratch && aligned(scratch, 16), "bad table or pointers");
+	RB_REQUIRE_TABLE(table, capacity);
+	RB_REQUIRE(frontier && count_dev && scratch && aligned(scratch, 16), "bad pointers");
 	RB_REQUIRE(aligned(next_frontier, 4), "next_frontier must be 4-byte aligned");
 	RB_INIT();
 	const int64_t items = 12 * n;
 	const rbf::Scratch sc = rbf::scratch_of(scratch, items);
 	cudaStream_t st = S(stream);
+	RB_CUDA(cudaMemsetAsync(sc.lost, 0, (size_t)rbf::control_bytes(items), st));
+	const int need_first = first != nullptr;
 	if (rep == RB_REP_2024) {
 		const rbf::FromParent2024 prov{frontier};
-		rbf::k_probe2024<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(prov, table, capacity, items, sc.slot);
+		rbf::k_probe2024<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(prov, table, capacity, items, need_first, sc.word, sc.lost, sc.ctl, seen, index);
 		RB_LAUNCHED("frontier_probe_2024");
-		int rc = frontier_common_tail(table, capacity, items, sc, seen, first, st);
-		if (rc != RB_OK) return rc;
-		rbf::k_assign2024<rbf::FromParent2024, true><<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(
-			prov, table, capacity, items, sc.slot, sc.block_new, count_dev, next_frontier, parent, action, solved);
-		RB_LAUNCHED("frontier_assign_2024");
+		rbf::k_resolve<rbf::FromParent2024, true><<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(
+			prov, table, capacity, items, need_first, sc.word, sc.lost, sc.status, sc.ctl, count_dev, n_new_dev, first, index, nullptr, next_frontier, parent,
+			action, solved);
+		RB_LAUNCHED("frontier_resolve_2024");
 	} else {
 		RB_REQUIRE(aligned(frontier, 16) && aligned(next_frontier, 16), "6x8x6 states must be 16-byte aligned");
 		int8_t* children = reinterpret_cast<int8_t*>(sc.keys + items);
 		int32_t* new_items = reinterpret_cast<int32_t*>(children + items * 288);
+		int32_t* n_new = n_new_dev ? n_new_dev : reinterpret_cast<int32_t*>(sc.ctl + 2);
 		int rc = rb_expand12(RB_REP_686, frontier, children, nullptr, nullptr, n, stream);
 		if (rc != RB_OK) return rc;
 		rbf::k_pack686<<<(unsigned)((items + 7) / 8), rbf::kThreads, 0, st>>>(children, items, sc.keys);
 		RB_LAUNCHED("frontier_pack_686");
-		rbf::k_probe_keys<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(sc.keys, table, capacity, items, sc.slot);
+		rbf::k_probe_keys<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(sc.keys, table, capacity, items, need_first, sc.word, sc.lost, sc.ctl, seen, index);
 		RB_LAUNCHED("frontier_probe_keys");
-		rc = frontier_common_tail(table, capacity, items, sc, seen, first, st);
-		if (rc != RB_OK) return rc;
-		rbf::k_assign_ids<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(table, capacity, items, sc.slot, sc.block_new, count_dev, new_items);
-		RB_LAUNCHED("frontier_assign");
-		rbf::k_gather686<<<rb_grid(items, 8, 8), rbf::kThreads, 0, st>>>(children, new_items, sc.block_new, sc.nb, next_frontier, parent,
-		                                                             action, solved);
+		rbf::k_resolve<rbf::NoProvider, false><<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(
+			rbf::NoProvider{}, table, capacity, items, need_first, sc.word, sc.lost, sc.status, sc.ctl, count_dev, n_new, first, index, new_items, nullptr,
+			nullptr, nullptr, nullptr);
+		RB_LAUNCHED("frontier_resolve");
+		rbf::k_gather686<<<rb_grid(items, 8, 8), rbf::kThreads, 0, st>>>(children, new_items, n_new, next_frontier, parent, action, solved);
 		RB_LAUNCHED("frontier_gather_686");
 	}
-	rbf::k_finish<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(table, capacity, items, sc.slot, index);
-	RB_LAUNCHED("frontier_finish");
-	rbf::k_bump<<<1, 1, 0, st>>>(count_dev, sc.block_new, sc.nb, n_new_dev);
-	RB_LAUNCHED("frontier_bump");
+	if (index) {
+		rbf::k_index_rest<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(table, capacity, items, sc.word, first, index);
+		RB_LAUNCHED("frontier_index_rest");
+	}
 	return RB_OK;
 }
 
@@ -516,8 +519,8 @@ static int astar_view(const rb_astar_view* a, rba::View& v) {
 	RB_REQUIRE(a->K > 0 && a->K <= 65535 && a->M > 1 && a->N > 0 && a->N <= 1024, "bad K / M / N (K <= 65535, N <= 1024)");
 	RB_REQUIRE(a->states && a->G && a->parents && a->parent_actions && a->cost && a->in_open && a->count && a->n_sel && a->sel && a->won &&
 	           a->solved_index && a->table && a->scratch, "null buffer in view");
-	RB_REQUIRE(pow2(a->capacity) && aligned(a->table, 16) && aligned(a->scratch, 16) && aligned(a->states, 4) && aligned(a->G, 8) && aligned(a->cost, 8),
-	           "misaligned buffer or capacity not a power of two");
+	RB_REQUIRE_TABLE(a->table, a->capacity);
+	RB_REQUIRE(aligned(a->scratch, 16) && aligned(a->states, 4) && aligned(a->G, 8) && aligned(a->cost, 8), "misaligned buffer");
 	const int64_t K = a->K, P = 12 * (int64_t)a->N, nbx = (P + rba::kThreads - 1) / rba::kThreads;
 	v.K = a->K; v.M = a->M; v.N = a->N;
 	v.states = a->states; v.G = a->G; v.parents = a->parents; v.parent_actions = a->parent_actions; v.cost = a->cost; v.in_open = a->in_open;

@@ -24,6 +24,15 @@ def _pow2_at_least(x: int) -> int:
 	return 1 << max(4, int(x - 1).bit_length())
 
 
+def read_count(t: torch.Tensor) -> int:
+	"""Host read of a device counter of the frontier kernels (`count`, `n_new`): -1 means a batch found the hash table full
+	(include/rubiks_b200.h, RB_ERR_CAPACITY semantics without a sync inside the call)."""
+	n = int(t.item())
+	if n < 0:
+		raise N.RubiksError(f"librubiks_b200 error {N.RB_ERR_CAPACITY}: the state hash set overflowed (table full); its contents are undefined")
+	return n
+
+
 class StateHashSet:
 	def __init__(self, capacity: int = 1 << 16, is2024: bool | None = None):
 		N.require_cuda()
@@ -45,7 +54,7 @@ class StateHashSet:
 		self._upper = 0
 
 	def __len__(self) -> int:
-		n = int(self.count.item())
+		n = read_count(self.count)
 		self._upper = n
 		return n
 
@@ -125,6 +134,9 @@ class StateHashSet:
 		return out
 
 
+LAST_LAYER_MS = []
+
+
 def bfs_layers(max_depth: int, start=None, is2024: bool | None = None, capacity: int | None = None):
 	"""Layer-synchronous BFS closure from `start` (default solved): per-depth counts of newly discovered states
 	(1, 12, 114, 1068, ... for the 20x24 cube) and the StateHashSet.  Everything but one int per layer stays on the device."""
@@ -135,11 +147,16 @@ def bfs_layers(max_depth: int, start=None, is2024: bool | None = None, capacity:
 	frontier, _ = hs._states(start)
 	hs.insert_unique(frontier)
 	counts = [1]
-	for _ in range(max_depth):
+	events = [torch.cuda.Event(enable_timing=True) for _ in range(max_depth + 1)]
+	events[0].record()
+	for d in range(max_depth):
 		out = hs.expand(frontier, parents=False, solved=False)
-		n_new = int(out["n_new"].item())
+		events[d + 1].record()
+		n_new = read_count(out["n_new"])
 		frontier = out["next"][:n_new]
 		counts.append(n_new)
+	global LAST_LAYER_MS
+	LAST_LAYER_MS = [events[d].elapsed_time(events[d + 1]) for d in range(max_depth)]      # device time per layer (diagnostics)
 	return counts, hs
 
 
@@ -196,7 +213,7 @@ class BFS(Agent):
 				# never more parents than the remaining budget could admit if each recorded a single new state ...
 				take = min(frontier.shape[0] - done, max(self._min_slice, max_states - total))
 				out = hs.expand(frontier[done:done + take])
-				n_new = int(out["n_new"].item())
+				n_new = read_count(out["n_new"])
 				parent = out["parent"][:n_new]
 				n_adm = n_new
 				if total + n_new >= max_states:
@@ -289,7 +306,7 @@ class AStar(Agent):
 			self.increase_stack_size()
 		idcs_dev = torch.from_numpy(expand_idcs).to(self.hs.dev)
 		out = self.hs.expand(self.states[idcs_dev], flags=True, index=True)
-		n_new = int(out["n_new"].item())
+		n_new = read_count(out["n_new"])
 		base = self.n_states
 		new_states = out["next"][:n_new]
 		self.states[base + 1:base + 1 + n_new] = new_states
@@ -418,7 +435,7 @@ class MCTS(Agent):
 		leaf_index = visited_states_idcs[-1]
 		out = self.hs.expand(self.states[leaf_index:leaf_index + 1], flags=True, index=True, parents=False)
 		substate_idcs = out["index"].cpu().numpy().astype(int)
-		n_new = int(out["n_new"].item())
+		n_new = read_count(out["n_new"])
 		new_substate_idcs = self.n_states + np.arange(n_new) + 1
 		new_substates = out["next"][:n_new]
 		self.states[self.n_states + 1:self.n_states + 1 + n_new] = new_substates

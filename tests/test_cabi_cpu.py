@@ -108,3 +108,14 @@ def test_missing_gpu_fails_loudly():
 		pytest.skip("GPU present")
 	with pytest.raises(N.RubiksError):
 		cube.multi_rotate(np.zeros((1, 20), np.int8), [0], [1])
+
+
+def test_hashset_capacity_limits_are_errors():
+	"""Slot numbers travel in 30 bits: a larger table is refused (RB_ERR_CAPACITY) before anything is launched."""
+	from rl_rubiks_b200 import _native as N
+	assert N.lib.rb_hashset_bytes(1 << 20) == 32 << 20
+	fake = ctypes.c_void_p(1 << 20)                                   # aligned, never dereferenced: the checks come first
+	assert N.lib.rb_hashset_clear(fake, 1 << 31, None) == N.RB_ERR_CAPACITY
+	assert N.lib.rb_hashset_clear(fake, (1 << 20) + 1, None) == N.RB_ERR_BAD_ARG
+	assert N.lib.rb_hashset_clear(ctypes.c_void_p((1 << 20) + 16), 1 << 20, None) == N.RB_ERR_BAD_ARG
+	assert N.lib.rb_hashset_rehash(fake, 1 << 10, fake, 1 << 31, None) == N.RB_ERR_CAPACITY

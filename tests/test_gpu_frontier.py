@@ -125,6 +125,34 @@ def test_bfs_depth7_known_answer():
 	assert (hs.lookup(cube.expand12(inner)) > 0).all()
 
 
+def test_full_table_is_reported_not_silent():
+	"""A batch that finds the table full sets the device counters to -1 (no sync inside the call); the mirror raises on the
+	next read.  Dropped items get index -1.  Through the C ABI directly, below the mirror's load-factor management."""
+	from rl_rubiks_b200 import _native as N
+	from rl_rubiks_b200.frontier import StateHashSet, read_count
+	hs = StateHashSet(64, True)
+	assert hs.capacity == 64
+	states = torch.from_numpy(_states(500, True, seed=3, depth=8)).cuda()
+	n = states.shape[0]
+	seen = torch.empty(n, dtype=torch.uint8, device="cuda"); first = torch.empty_like(seen)
+	index = torch.empty(n, dtype=torch.int32, device="cuda")
+	scratch = torch.empty(N.lib.rb_hashset_scratch_bytes(n), dtype=torch.uint8, device="cuda")
+	N.check(N.lib.rb_hashset_insert_unique(hs.rep, N.ptr(hs.table), hs.capacity, N.ptr(states), n, N.ptr(hs.count), N.ptr(seen), N.ptr(first),
+										   N.ptr(index), N.ptr(scratch), N.stream_handle()))
+	assert int(hs.count.item()) == -1 and int((index == -1).sum().item()) >= n - 64
+	with pytest.raises(N.RubiksError):
+		len(hs)
+	# the error is sticky on that counter
+	N.check(N.lib.rb_hashset_insert_unique(hs.rep, N.ptr(hs.table), hs.capacity, N.ptr(states[:4]), 4, N.ptr(hs.count), None, None, None,
+										   N.ptr(scratch), N.stream_handle()))
+	with pytest.raises(N.RubiksError):
+		read_count(hs.count)
+	# the mirror itself never gets there: it grows the table first
+	hs2 = StateHashSet(16, True)
+	_, first2, idx2 = hs2.insert_unique(states)
+	assert len(hs2) == int(first2.sum().item()) and int(idx2.min().item()) >= 1
+
+
 class _FakeNet(torch.nn.Module):
 	def __init__(self, w, quant=4.0):
 		super().__init__()
