@@ -26,6 +26,7 @@
 #pragma once
 #include "rb_common.cuh"
 #include "rb_tables.cuh"
+#include <cuda.h>              // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <stdlib.h>
 
 namespace rbs {
@@ -180,6 +181,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
 	             "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+	             : "memory");
+}
+
+// 2-D tensor copy global -> shared (TMA; SASS UTMALDG): box {32 cubes, h moves} of the move-major action array at (x = first
+// cube, y = first move), written row by row (32 bytes per move), completion counted in bytes on `bar`.
+__device__ __forceinline__ void tma_2d_g2s(void* dst_smem, const CUtensorMap* map, int32_t x, int32_t y, uint64_t* bar) {
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst_smem)),
+	             "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
 	             : "memory");
 }
 
@@ -433,10 +442,16 @@ __device__ __forceinline__ void cubie_major(const Slots& s, uint32_t (&w)[5]) {
 // kMode: 0 = any depth (unaligned rows, funnel-shifted words), 1 = depth % 4 == 0 (word loads), 2 = depth % 16 == 0 (16-byte
 // loads in the main loop), 3 = depth % 128 == 0 (16-byte loads from padded rows).  Separate instantiations keep the common
 // mode-1 kernel (depth 100) free of the other modes' code.
-template <int kMode, int R2>
+// kT (needs kMode <= 1): the actions are MOVE-major, uint8 [depth][n] -- the reference's own draw shape (cube.py:226-227).  A
+// warp's tile is then depth rows of 32 bytes, fetched by one 2-D tensor copy (TMA, box {32 cubes, depth moves}) into
+// [move][cube] order: the action words of four consecutive moves are one LINEAR word load per lane (bank-conflict free for
+// every depth) followed by a 4 x 4 byte transpose among the four lanes that share a column (two shuffles, two PRMT); lane l
+// then works on cube 4 (l % 8) + l / 8 of the chunk.
+// n_work <= blockDim.x / 32 warps take chunks (small n is spread over all SMs); the whole CTA stages the table.
+template <int kMode, int R2, bool kT = false>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out, int64_t n, int depth, int out_pitch,
-                  uint32_t p2_stride) {
+                  uint32_t p2_stride, uint32_t n_work, const __grid_constant__ CUtensorMap tmap, int box_h) {
 	// p2_stride = 4 * R2 arrives as a kernel argument so that the twist|flip word's address is an IMAD (FMA pipe) rather than
 	// the LEA (ALU pipe, the binding one) ptxas emits for a power-of-two constant
 	constexpr bool kWordAligned = kMode >= 1;
@@ -445,7 +460,7 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 	uint8_t* table = smem;                                              // [P1 | P2 | tail | mbarriers | action buffers]
 	uint8_t* tail = smem + kP1Bytes3 + kP2Bytes3;
 	uint64_t* bars = reinterpret_cast<uint64_t*>(tail + kTailBytes);
-	const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+	const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5, n_warps = n_work;
 	const int chunk_bytes = 32 * depth;
 	// depth % 16 == 0: the main loop reads the action rows with 16-byte loads (a16).  depth % 128 == 0: the rows are 128 bytes
 	// apart or a multiple, every lane in the same bank group (8-way conflicts even for 16-byte loads, 32-way for words); those
@@ -453,9 +468,11 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 	// rows of pitch depth + 16, whose 16-byte stride is odd: conflict free.  Measured, 2^24 cubes: depth 64 1.00 -> 0.76 ms,
 	// 96 1.08 -> 0.82 ms (16-byte loads), 128 2.91 -> 1.33 ms (padded rows).
 	constexpr bool a16 = kMode >= 2, pad16 = kMode == 3;
-	const int pitch = depth + (pad16 ? 16 : 0);
+	static_assert(!kT || kMode <= 1, "move-major tiles use the word / byte modes");
+	const int pitch = kT ? ((depth + 3) & ~3) : depth + (pad16 ? 16 : 0);     // kT: warp buffers stay 128-byte aligned (TMA destination)
 	uint8_t* buf = reinterpret_cast<uint8_t*>(bars) + kMaxThreads / 32 * 8 + (size_t)wib * (32 * pitch);
 	uint64_t* bar = &bars[wib];
+	const uint32_t my_cube = kT ? 4u * (lane & 7u) + (lane >> 3) : lane;       // the cube of the chunk this lane works on
 	const uint32_t off1 = smem_u32(table) + (lane & (kRep1 - 1)) * 16u, off2 = smem_u32(table) + (uint32_t)kP1Bytes3 + (lane & (R2 - 1)) * 4u;
 
 	const int64_t n_chunks = (n + 31) / 32;
@@ -465,7 +482,12 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 	auto issue = [&](int64_t c) {                             // warp-wide: starts the bulk copy (copies) of chunk c into this warp's buffer
 		if (c >= n_chunks) return;
 		const int cnt = (int)min((int64_t)32, n - c * 32);
-		if (pad16) {
+		if (kT) {                                                 // cubes past n are zero filled by the copy engine (action 0)
+			if (lane == 0) {
+				mbar_expect_tx(bar, (uint32_t)chunk_bytes);
+				for (int y = 0; y < depth; y += box_h) tma_2d_g2s(buf + y * 32, &tmap, (int32_t)(c * 32), y, bar);
+			}
+		} else if (pad16) {
 			if (lane == 0) mbar_expect_tx(bar, (uint32_t)(cnt * depth));
 			__syncwarp();
 			if ((int)lane < cnt) bulk_g2s(buf + lane * pitch, actions + c * chunk_bytes + (int64_t)lane * depth, (uint32_t)depth, bar);
@@ -480,7 +502,7 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 	if (lane == 0) mbar_init(bar, 1);
 	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	__syncwarp();
-	issue(chunk);
+	if (wib < n_work) issue(chunk);
 	for (int i = threadIdx.x; i < kP2Rows3 * kRep1; i += blockDim.x) {
 		const int row = i / kRep1, c = i % kRep1;
 		if (row < kRows3) {
@@ -497,19 +519,22 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 		*reinterpret_cast<uint32_t*>(tail + i * 32 + 16) = r[4];
 	}
 	__syncthreads();
+	if (wib >= n_work) return;
 
 	uint32_t parity = 0;
+	// kT: selectors of the 4 x 4 byte transpose (lane = 8 r + c holds row r of column word c; see word_at)
+	const uint32_t tsel_a = (lane & 16u) ? 0x3276u : 0x5410u, tsel_b = (lane & 8u) ? 0x3715u : 0x6240u;
 	for (; chunk < n_chunks; chunk += stride) {
 		const int cnt = (int)min((int64_t)32, n - chunk * 32);
-		const int bytes = cnt * depth, bulk = bytes & ~15;
-		if (bulk < bytes) {
+		const int bytes = cnt * depth, bulk = kT ? chunk_bytes : (bytes & ~15);
+		if (!kT && bulk < bytes) {
 			if ((int)lane < bytes - bulk) buf[bulk + lane] = actions[chunk * chunk_bytes + bulk + lane];
 			__syncwarp();
 		}
 		if (bulk) { mbar_wait(bar, parity); parity ^= 1u; }
 
 		uint32_t res[5] = {0u, 0u, 0u, 0u, 0u};
-		if ((int)lane < cnt) {
+		if (kT || (int)lane < cnt) {                                      // kT: every lane runs (the transposes shuffle across the warp)
 			uint8_t* row = buf + lane * pitch;
 			Slots s{0x60402000u, 0xe0c0a080u, 0x03020100u, 0x07060504u, 0x0b0a0908u};
 			// depth % 4 != 0: rows start at any byte; two aligned words and one funnel shift give the four action bytes at m
@@ -518,6 +543,15 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 			const uint32_t* arow = reinterpret_cast<const uint32_t*>(buf + ((lane * depth) & ~3));
 			const uint32_t ashift = ((lane * depth) & 3) * 8;
 			auto word_at = [&](int m) -> uint32_t {
+				if (kT) {
+					// rows m .. m+3 of the [move][cube] tile are 128 linear bytes: lane 8 r + c loads word c of row m + r, the four
+					// lanes of a column transpose their 4 x 4 bytes: result = moves m .. m+3 of cube 4 c + r
+					uint32_t w = reinterpret_cast<const uint32_t*>(buf)[m * 8 + (int)lane];
+					uint32_t t = __shfl_xor_sync(0xffffffffu, w, 16);
+					w = prmt(w, t, tsel_a);
+					t = __shfl_xor_sync(0xffffffffu, w, 8);
+					return prmt(w, t, tsel_b);
+				}
 				if (kWordAligned) return *reinterpret_cast<const uint32_t*>(row + m);
 				return __funnelshift_r(arow[m >> 2], arow[(m >> 2) + 1], ashift);
 			};
@@ -537,7 +571,7 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 				apply3(__dp4a(w1, 0x0000010Cu, __dp4a(w0, 0x90000000u, 0u)));
 				apply3(__dp4a(w0, 0x00010C90u, 0u));
 			};
-			auto inv_at = [&](int m) -> uint32_t { return row[m] & 15u; };     // raw action: the tables are indexed by it
+			auto inv_at = [&](int m) -> uint32_t { return (kT ? buf[m * 32 + (int)my_cube] : row[m]) & 15u; };     // raw action: the tables are indexed by it
 			// the depth % 24 moves at the end of the sequence come first: at most 4 + 3 + 1 rows (8 byte-fetched rows when unaligned)
 			const int M = depth - depth % 24;
 			auto apply_tail = [&](uint32_t idx2) {                             // 2-move row (second move may be the identity, 12)
@@ -610,8 +644,8 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 			cubie_major(s, res);
 		}
 		__syncwarp();                                                     // every lane's action row is consumed: the buffer head is free
-		if ((int)lane < cnt) {
-			uint32_t* dst_row = reinterpret_cast<uint32_t*>(buf + lane * 20);   // results packed [cube][20] at the head of the warp's buffer
+		if ((int)my_cube < cnt) {
+			uint32_t* dst_row = reinterpret_cast<uint32_t*>(buf + my_cube * 20);   // results packed [cube][20] at the head of the warp's buffer
 #pragma unroll
 			for (int k = 0; k < 5; ++k) dst_row[k] = res[k];
 		}
@@ -688,6 +722,8 @@ static int ensure_device() {
 	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro3<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
 	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro3<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
 	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro3<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro3<0, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro3<1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
 	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
 	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
 	done[dev] = true;
@@ -708,10 +744,12 @@ static int warps_for(int64_t n, int depth) {
 
 // 3-move kernel: fixed shared memory and warps per CTA for a given depth (0: use the 2-move kernel)
 static int64_t fixed_smem3(int r2) { return (int64_t)kP1Bytes3 + (int64_t)kP2Rows3 * 4 * r2 + kTailBytes + kMaxThreads / 32 * 8; }
-static int pitch3(int depth) { return depth % 128 == 0 ? depth + 16 : depth; }     // row pitch of the action buffers (see the kernel)
-static int warps_for3(int64_t n, int depth, int r2) {
+constexpr int kStageThreads = 1024;             // threads that fill the table, whatever the number of working warps
+// row pitch of the action buffers (see the kernel): move-major tiles are padded to whole words, depth % 128 == 0 rows by 16 bytes
+static int pitch3(int depth, bool transposed = false) { return transposed ? (depth + 3) / 4 * 4 : (depth % 128 == 0 ? depth + 16 : depth); }
+static int warps_for3(int64_t n, int depth, int r2, bool transposed = false) {
 	if (depth < 20) return 0;
-	int64_t w = (kSmemBudget - 16 - fixed_smem3(r2)) / (32 * (int64_t)pitch3(depth));
+	int64_t w = (kSmemBudget - 16 - fixed_smem3(r2)) / (32 * (int64_t)pitch3(depth, transposed));
 	if (w > max_threads() / 32) w = max_threads() / 32;
 	if (w < 8) return 0;                         // long sequences: too few resident warps to hide the table latency
 	const int64_t spread = ((n + 31) / 32 + RB_NUM_SMS - 1) / RB_NUM_SMS;
@@ -719,26 +757,73 @@ static int warps_for3(int64_t n, int depth, int r2) {
 	return (int)w;
 }
 
-static int launch(const uint8_t* actions, int8_t* out, int64_t n, int depth, cudaStream_t st, int out_pitch = 20) {
+// cuTensorMapEncodeTiled through the runtime (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+	static EncodeTiledFn fn = [] {
+		void* p = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+		return reinterpret_cast<EncodeTiledFn>(p);
+	}();
+	return fn;
+}
+
+// Box height of the move-major tile copies: the whole depth when it fits one box (<= 256 rows), else an even split into boxes
+// whose height is a multiple of 4 rows (every box must land 128-byte aligned in shared memory); 0 = none.
+static int box_height(int depth) {
+	if (depth <= 256) return depth;
+	for (int k = (depth + 255) / 256; k <= 16; ++k)
+		if (depth % k == 0 && (depth / k) % 4 == 0) return depth / k;
+	return 0;
+}
+
+// Can the move-major ([depth][n]) fast path take this call?
+static bool can_transposed(const uint8_t* actions, int64_t n, int depth) {
+	return depth >= 20 && n % 16 == 0 && (reinterpret_cast<uintptr_t>(actions) & 15u) == 0 && box_height(depth) > 0 && encode_tiled_fn() != nullptr;
+}
+
+// actions: cube-major uint8 [n][depth], or move-major uint8 [depth][n] when `transposed` (see can_transposed)
+static int launch(const uint8_t* actions, int8_t* out, int64_t n, int depth, cudaStream_t st, int out_pitch = 20, bool transposed = false) {
 	int rc = ensure_device();
 	if (rc != RB_OK) return rc;
 	static const int rows_per = env_int("RB_SCRAMBLE_MOVES_PER_ROW", 3), r2_env = env_int("RB_SCRAMBLE_R2", 1);
-	const int r2 = (depth % 4 == 0 && depth % 16 != 0 && (r2_env == 2 || r2_env == 4)) ? r2_env : 1;
-	const int W3 = rows_per == 3 ? warps_for3(n, depth, r2) : 0;
+	const int r2 = (!transposed && depth % 4 == 0 && depth % 16 != 0 && (r2_env == 2 || r2_env == 4)) ? r2_env : 1;
+	const int W3 = rows_per == 3 || transposed ? warps_for3(n, depth, r2, transposed) : 0;
+	CUtensorMap tmap;
+	memset(&tmap, 0, sizeof(tmap));
 	if (W3 > 0) {
 		const int64_t ctas = ((n + 31) / 32 + W3 - 1) / W3;
 		const int grid = (int)(ctas < RB_NUM_SMS ? ctas : RB_NUM_SMS);
-		size_t smem = (size_t)fixed_smem3(r2) + (size_t)W3 * 32 * pitch3(depth) + 16;
+		// the table is staged by a full CTA however few warps have work (4096 cubes: 128 single-warp CTAs took 70 us to fill it)
+		const int threads = W3 * 32 < kStageThreads ? kStageThreads : W3 * 32;
+		size_t smem = (size_t)fixed_smem3(r2) + (size_t)W3 * 32 * pitch3(depth, transposed) + 16;
 		if (smem < (size_t)kMinSmem3) smem = kMinSmem3;
-		if (depth % 4 != 0) k_scramble_macro3<0, 1><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch, 4u);
-		else if (depth % 128 == 0) k_scramble_macro3<3, 1><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch, 4u);
-		else if (depth % 16 == 0) k_scramble_macro3<2, 1><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch, 4u);
-		else if (r2 == 2) k_scramble_macro3<1, 2><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch, 8u);
-		else if (r2 == 4) k_scramble_macro3<1, 4><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch, 16u);
-		else k_scramble_macro3<1, 1><<<grid, W3 * 32, smem, st>>>(actions, out, n, depth, out_pitch, 4u);
+		const uint32_t nw = (uint32_t)W3;
+		if (transposed) {
+			const int bh = box_height(depth);
+			const cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)depth}, gstride[1] = {(cuuint64_t)n};
+			const cuuint32_t box[2] = {32u, (cuuint32_t)bh}, estride[2] = {1u, 1u};
+			const CUresult cr = encode_tiled_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(actions), gdim, gstride, box, estride,
+			                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+			                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+			if (cr != CUDA_SUCCESS) return rb_fail(RB_ERR_CUDA, "cuTensorMapEncodeTiled failed for the move-major action array%s%s");
+			if (depth % 4 != 0) k_scramble_macro3<0, 1, true><<<grid, threads, smem, st>>>(actions, out, n, depth, out_pitch, 4u, nw, tmap, bh);
+			else k_scramble_macro3<1, 1, true><<<grid, threads, smem, st>>>(actions, out, n, depth, out_pitch, 4u, nw, tmap, bh);
+			RB_LAUNCHED("scramble_macro3t_2024");
+			return RB_OK;
+		}
+		if (depth % 4 != 0) k_scramble_macro3<0, 1><<<grid, threads, smem, st>>>(actions, out, n, depth, out_pitch, 4u, nw, tmap, 0);
+		else if (depth % 128 == 0) k_scramble_macro3<3, 1><<<grid, threads, smem, st>>>(actions, out, n, depth, out_pitch, 4u, nw, tmap, 0);
+		else if (depth % 16 == 0) k_scramble_macro3<2, 1><<<grid, threads, smem, st>>>(actions, out, n, depth, out_pitch, 4u, nw, tmap, 0);
+		else if (r2 == 2) k_scramble_macro3<1, 2><<<grid, threads, smem, st>>>(actions, out, n, depth, out_pitch, 8u, nw, tmap, 0);
+		else if (r2 == 4) k_scramble_macro3<1, 4><<<grid, threads, smem, st>>>(actions, out, n, depth, out_pitch, 16u, nw, tmap, 0);
+		else k_scramble_macro3<1, 1><<<grid, threads, smem, st>>>(actions, out, n, depth, out_pitch, 4u, nw, tmap, 0);
 		RB_LAUNCHED("scramble_macro3_2024");
 		return RB_OK;
 	}
+	if (transposed) return rb_fail(RB_ERR_BAD_ARG, "move-major fast path does not apply%s%s");
 	const int W = warps_for(n, depth);
 	const int64_t ctas = ((n + 31) / 32 + W - 1) / W;
 	const int grid = (int)(ctas < RB_NUM_SMS ? ctas : RB_NUM_SMS);

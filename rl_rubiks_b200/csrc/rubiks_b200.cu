@@ -198,6 +198,15 @@ int rb_scramble(int rep, const uint8_t* actions, int64_t stride_cube, int64_t st
 			RB_LAUNCHED("compose_2024");
 			return RB_OK;
 		}
+		if (depth > 0 && stride_cube == 1 && stride_move == n && start != out && rbs::can_transposed(actions, n, depth) &&
+		    rbs::warps_for3(n, depth, 1, true) > 0) {
+			// move-major actions [depth][n], the reference's draw shape (cube.py:226-227): 2-D tensor copies + in-register transposes
+			int rc = rbs::launch(actions, out, n, depth, S(stream), 20, true);
+			if (rc != RB_OK || !start) return rc;
+			rb2024::k_compose<<<rb_grid(n, 8, 8), rb2024::kThreads, 0, S(stream)>>>(out, start, n);
+			RB_LAUNCHED("compose_2024");
+			return RB_OK;
+		}
 		rb2024::k_scramble<<<rb_grid(n, rb2024::kThreads, 8), rb2024::kThreads, 0, S(stream)>>>(
 			actions, stride_cube, stride_move, start, out, n, depth);
 		RB_LAUNCHED("scramble_2024");
@@ -208,6 +217,14 @@ int rb_scramble(int rep, const uint8_t* actions, int64_t stride_cube, int64_t st
 			// net permutation of the sequence on the slot-major macro-move kernel (20x24 state parked at the head of each
 			// output row), then one gather of the start state's sticker records through it
 			int rc = rbs::launch(actions, out, n, depth, S(stream), rb686::kStateBytes);
+			if (rc != RB_OK) return rc;
+			rb686::k_render_from2024<<<rb_grid((n + 31) / 32, rb686::kWarps, 8), rb686::kThreads, 0, S(stream)>>>(out, start, n);
+			RB_LAUNCHED("render_686");
+			return RB_OK;
+		}
+		if (depth > 0 && stride_cube == 1 && stride_move == n && start != out && rbt::host().stickers_ok && rbs::can_transposed(actions, n, depth) &&
+		    rbs::warps_for3(n, depth, 1, true) > 0) {
+			int rc = rbs::launch(actions, out, n, depth, S(stream), rb686::kStateBytes, true);
 			if (rc != RB_OK) return rc;
 			rb686::k_render_from2024<<<rb_grid((n + 31) / 32, rb686::kWarps, 8), rb686::kThreads, 0, S(stream)>>>(out, start, n);
 			RB_LAUNCHED("render_686");
