@@ -442,16 +442,11 @@ __device__ __forceinline__ void cubie_major(const Slots& s, uint32_t (&w)[5]) {
 // kMode: 0 = any depth (unaligned rows, funnel-shifted words), 1 = depth % 4 == 0 (word loads), 2 = depth % 16 == 0 (16-byte
 // loads in the main loop), 3 = depth % 128 == 0 (16-byte loads from padded rows).  Separate instantiations keep the common
 // mode-1 kernel (depth 100) free of the other modes' code.
-// kT (needs kMode <= 1): the actions are MOVE-major, uint8 [depth][n] -- the reference's own draw shape (cube.py:226-227).  A
-// warp's tile is then depth rows of 32 bytes, fetched by one 2-D tensor copy (TMA, box {32 cubes, depth moves}) into
-// [move][cube] order: the action words of four consecutive moves are one LINEAR word load per lane (bank-conflict free for
-// every depth) followed by a 4 x 4 byte transpose among the four lanes that share a column (two shuffles, two PRMT); lane l
-// then works on cube 4 (l % 8) + l / 8 of the chunk.
 // n_work <= blockDim.x / 32 warps take chunks (small n is spread over all SMs); the whole CTA stages the table.
-template <int kMode, int R2, bool kT = false>
+template <int kMode, int R2>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out, int64_t n, int depth, int out_pitch,
-                  uint32_t p2_stride, uint32_t n_work, const __grid_constant__ CUtensorMap tmap, int box_h) {
+                  uint32_t p2_stride, uint32_t n_work) {
 	// p2_stride = 4 * R2 arrives as a kernel argument so that the twist|flip word's address is an IMAD (FMA pipe) rather than
 	// the LEA (ALU pipe, the binding one) ptxas emits for a power-of-two constant
 	constexpr bool kWordAligned = kMode >= 1;
@@ -468,11 +463,9 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 	// rows of pitch depth + 16, whose 16-byte stride is odd: conflict free.  Measured, 2^24 cubes: depth 64 1.00 -> 0.76 ms,
 	// 96 1.08 -> 0.82 ms (16-byte loads), 128 2.91 -> 1.33 ms (padded rows).
 	constexpr bool a16 = kMode >= 2, pad16 = kMode == 3;
-	static_assert(!kT || kMode <= 1, "move-major tiles use the word / byte modes");
-	const int pitch = kT ? ((depth + 3) & ~3) : depth + (pad16 ? 16 : 0);     // kT: warp buffers stay 128-byte aligned (TMA destination)
+	const int pitch = depth + (pad16 ? 16 : 0);
 	uint8_t* buf = reinterpret_cast<uint8_t*>(bars) + kMaxThreads / 32 * 8 + (size_t)wib * (32 * pitch);
 	uint64_t* bar = &bars[wib];
-	const uint32_t my_cube = kT ? 4u * (lane & 7u) + (lane >> 3) : lane;       // the cube of the chunk this lane works on
 	const uint32_t off1 = smem_u32(table) + (lane & (kRep1 - 1)) * 16u, off2 = smem_u32(table) + (uint32_t)kP1Bytes3 + (lane & (R2 - 1)) * 4u;
 
 	const int64_t n_chunks = (n + 31) / 32;
@@ -482,12 +475,7 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 	auto issue = [&](int64_t c) {                             // warp-wide: starts the bulk copy (copies) of chunk c into this warp's buffer
 		if (c >= n_chunks) return;
 		const int cnt = (int)min((int64_t)32, n - c * 32);
-		if (kT) {                                                 // cubes past n are zero filled by the copy engine (action 0)
-			if (lane == 0) {
-				mbar_expect_tx(bar, (uint32_t)chunk_bytes);
-				for (int y = 0; y < depth; y += box_h) tma_2d_g2s(buf + y * 32, &tmap, (int32_t)(c * 32), y, bar);
-			}
-		} else if (pad16) {
+		if (pad16) {
 			if (lane == 0) mbar_expect_tx(bar, (uint32_t)(cnt * depth));
 			__syncwarp();
 			if ((int)lane < cnt) bulk_g2s(buf + lane * pitch, actions + c * chunk_bytes + (int64_t)lane * depth, (uint32_t)depth, bar);
@@ -522,19 +510,17 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 	if (wib >= n_work) return;
 
 	uint32_t parity = 0;
-	// kT: selectors of the 4 x 4 byte transpose (lane = 8 r + c holds row r of column word c; see word_at)
-	const uint32_t tsel_a = (lane & 16u) ? 0x3276u : 0x5410u, tsel_b = (lane & 8u) ? 0x3715u : 0x6240u;
 	for (; chunk < n_chunks; chunk += stride) {
 		const int cnt = (int)min((int64_t)32, n - chunk * 32);
-		const int bytes = cnt * depth, bulk = kT ? chunk_bytes : (bytes & ~15);
-		if (!kT && bulk < bytes) {
+		const int bytes = cnt * depth, bulk = bytes & ~15;
+		if (bulk < bytes) {
 			if ((int)lane < bytes - bulk) buf[bulk + lane] = actions[chunk * chunk_bytes + bulk + lane];
 			__syncwarp();
 		}
 		if (bulk) { mbar_wait(bar, parity); parity ^= 1u; }
 
 		uint32_t res[5] = {0u, 0u, 0u, 0u, 0u};
-		if (kT || (int)lane < cnt) {                                      // kT: every lane runs (the transposes shuffle across the warp)
+		if ((int)lane < cnt) {
 			uint8_t* row = buf + lane * pitch;
 			Slots s{0x60402000u, 0xe0c0a080u, 0x03020100u, 0x07060504u, 0x0b0a0908u};
 			// depth % 4 != 0: rows start at any byte; two aligned words and one funnel shift give the four action bytes at m
@@ -543,15 +529,6 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 			const uint32_t* arow = reinterpret_cast<const uint32_t*>(buf + ((lane * depth) & ~3));
 			const uint32_t ashift = ((lane * depth) & 3) * 8;
 			auto word_at = [&](int m) -> uint32_t {
-				if (kT) {
-					// rows m .. m+3 of the [move][cube] tile are 128 linear bytes: lane 8 r + c loads word c of row m + r, the four
-					// lanes of a column transpose their 4 x 4 bytes: result = moves m .. m+3 of cube 4 c + r
-					uint32_t w = reinterpret_cast<const uint32_t*>(buf)[m * 8 + (int)lane];
-					uint32_t t = __shfl_xor_sync(0xffffffffu, w, 16);
-					w = prmt(w, t, tsel_a);
-					t = __shfl_xor_sync(0xffffffffu, w, 8);
-					return prmt(w, t, tsel_b);
-				}
 				if (kWordAligned) return *reinterpret_cast<const uint32_t*>(row + m);
 				return __funnelshift_r(arow[m >> 2], arow[(m >> 2) + 1], ashift);
 			};
@@ -571,7 +548,7 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 				apply3(__dp4a(w1, 0x0000010Cu, __dp4a(w0, 0x90000000u, 0u)));
 				apply3(__dp4a(w0, 0x00010C90u, 0u));
 			};
-			auto inv_at = [&](int m) -> uint32_t { return (kT ? buf[m * 32 + (int)my_cube] : row[m]) & 15u; };     // raw action: the tables are indexed by it
+			auto inv_at = [&](int m) -> uint32_t { return row[m] & 15u; };     // raw action: the tables are indexed by it
 			// the depth % 24 moves at the end of the sequence come first: at most 4 + 3 + 1 rows (8 byte-fetched rows when unaligned)
 			const int M = depth - depth % 24;
 			auto apply_tail = [&](uint32_t idx2) {                             // 2-move row (second move may be the identity, 12)
@@ -644,8 +621,8 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 			cubie_major(s, res);
 		}
 		__syncwarp();                                                     // every lane's action row is consumed: the buffer head is free
-		if ((int)my_cube < cnt) {
-			uint32_t* dst_row = reinterpret_cast<uint32_t*>(buf + my_cube * 20);   // results packed [cube][20] at the head of the warp's buffer
+		if ((int)lane < cnt) {
+			uint32_t* dst_row = reinterpret_cast<uint32_t*>(buf + lane * 20);   // results packed [cube][20] at the head of the warp's buffer
 #pragma unroll
 			for (int k = 0; k < 5; ++k) dst_row[k] = res[k];
 		}
@@ -690,6 +667,164 @@ k_scramble_macro3(const uint8_t* __restrict__ actions, int8_t* __restrict__ out,
 	}
 }
 
+// ---- move-major actions ---------------------------------------------------------------------------------------------------------
+// The reference draws its scrambles as faces / dirs of shape (depth, games) (cube.py:226-227): MOVE-major, uint8 [depth][n].
+// Work unit = a span of 128 consecutive cubes = one quad of four warps.  The quad's tile is depth rows of 128 bytes fetched
+// by 2-D tensor copies (TMA, box {128 cubes, <= 256 moves}; 32-byte rows -- a tile per warp -- cap the copy engine at one
+// row request per ~8 clocks and cost 1.49 ms for 2^24 x 100 moves).  Shared-memory banks are the word COLUMN of the tile
+// whatever the row, so the conflict-free read is a whole row per instruction: lane l takes word l of rows m .. m+3 (four
+// LDS.32) and holds moves m .. m+3 of cubes 4 l .. 4 l + 3 as a 4 x 4 byte matrix; warp k of the quad transposes out column
+// k (three PRMT with warp-uniform selectors) and works on cube 4 l + k.  The rest is k_scramble_macro3's modes 0 / 1.
+constexpr int kSpan = 128;
+__device__ __forceinline__ void quad_sync(uint32_t quad) {
+	asm volatile("bar.sync %0, 128;" ::"r"(quad + 1u) : "memory");
+}
+
+template <bool kWords>                                   // depth % 4 == 0: the remainder is whole action words too
+__global__ void __launch_bounds__(kMaxThreads, 1)
+k_scramble_mm(const __grid_constant__ CUtensorMap tmap, int8_t* __restrict__ out, int64_t n, int depth, int out_pitch, uint32_t p2_stride,
+              uint32_t n_quads, int box_h) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	constexpr int kP2Bytes3 = kP2Rows3 * 4;
+	uint8_t* table = smem;                                              // [P1 | P2 | tail | mbarriers | one tile per quad]
+	uint8_t* tail = smem + kP1Bytes3 + kP2Bytes3;
+	uint64_t* bars = reinterpret_cast<uint64_t*>(tail + kTailBytes);
+	const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5, quad = wib >> 2, k = wib & 3u, tq = threadIdx.x & 127u;
+	const int span_bytes = kSpan * depth;
+	uint8_t* tile = reinterpret_cast<uint8_t*>(bars) + kMaxThreads / 32 * 8 + (size_t)quad * span_bytes;
+	uint64_t* bar = &bars[quad];
+	const uint32_t off1 = smem_u32(table) + (lane & (kRep1 - 1)) * 16u, off2 = smem_u32(table) + (uint32_t)kP1Bytes3;
+	const int64_t n_spans = (n + kSpan - 1) / kSpan, stride = (int64_t)gridDim.x * n_quads;
+	int64_t span = (int64_t)blockIdx.x * n_quads + quad;
+
+	auto issue = [&](int64_t sp) {                            // one thread of the quad; cubes past n are zero filled (action 0)
+		if (sp >= n_spans) return;
+		mbar_expect_tx(bar, (uint32_t)span_bytes);
+		for (int y = 0; y < depth; y += box_h) tma_2d_g2s(tile + y * kSpan, &tmap, (int32_t)(sp * kSpan), y, bar);
+	};
+	if (tq == 0) mbar_init(bar, 1);
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	if (tq == 0 && quad < n_quads) issue(span);                            // the thread that initialised the barrier; the others meet it after the block barrier
+	for (int i = threadIdx.x; i < kP2Rows3 * kRep1; i += blockDim.x) {
+		const int row = i / kRep1, c = i % kRep1;
+		if (row < kRows3) {
+			const uint32_t* r = g_macro3 + row * kRowWords;
+			*reinterpret_cast<uint4*>(table + (row * kRep1 + c) * 16) = make_uint4(r[0], r[1], r[2], r[3]);
+			if (c == 0) *reinterpret_cast<uint32_t*>(table + kP1Bytes3 + row * 4) = r[4];
+		} else if (c == 0) {
+			*reinterpret_cast<uint32_t*>(table + kP1Bytes3 + row * 4) = 0u;
+		}
+	}
+	for (int i = threadIdx.x; i < kDevRows; i += blockDim.x) {
+		const uint32_t* r = g_macro_tail_inv + (i < kRows ? i : kRows - 1) * kRowWords;
+		*reinterpret_cast<uint4*>(tail + i * 32) = make_uint4(r[0], r[1], r[2], r[3]);
+		*reinterpret_cast<uint32_t*>(tail + i * 32 + 16) = r[4];
+	}
+	__syncthreads();
+	if (quad >= n_quads) return;
+
+	const uint32_t sel1 = k < 2 ? 0x5140u : 0x7362u, sel2 = (k & 1u) ? 0x7632u : 0x5410u;   // column k of a 4 x 4 byte matrix
+	const uint32_t my_cube = 4u * lane + k;                                                 // within the span
+	const uint32_t* tilew = reinterpret_cast<const uint32_t*>(tile);
+	uint32_t parity = 0;
+	for (; span < n_spans; span += stride) {
+		const int cnt = (int)min((int64_t)kSpan, n - span * kSpan);
+		mbar_wait(bar, parity); parity ^= 1u;
+
+		uint32_t res[5];
+		{
+			Slots s{0x60402000u, 0xe0c0a080u, 0x03020100u, 0x07060504u, 0x0b0a0908u};
+			auto word_at = [&](int m) -> uint32_t {                            // action bytes m .. m+3 of this lane's cube (m % 4 == 0)
+				const uint32_t* p = tilew + m * 32 + (int)lane;
+				const uint32_t x = prmt(p[0], p[32], sel1), y = prmt(p[64], p[96], sel1);
+				return prmt(x, y, sel2);
+			};
+			auto inv_at = [&](int m) -> uint32_t { return tile[m * kSpan + (int)my_cube] & 15u; };
+			auto apply3 = [&](uint32_t r) {
+				const uint32_t o1 = mad_u32(r, 16u * kRep1, off1), o2 = mad_u32(r, p2_stride, off2);
+				apply_row(lds128(o1), lds32(o2), s);
+			};
+			auto apply_words = [&](uint32_t w0, uint32_t w1, uint32_t w2) {      // 12 moves, last first (see k_scramble_macro3)
+				w0 &= 0x0f0f0f0fu; w1 &= 0x0f0f0f0fu; w2 &= 0x0f0f0f0fu;
+				apply3(__dp4a(w2, 0x010C9000u, 0u));
+				apply3(__dp4a(w2, 0x00000001u, __dp4a(w1, 0x0C900000u, 0u)));
+				apply3(__dp4a(w1, 0x0000010Cu, __dp4a(w0, 0x90000000u, 0u)));
+				apply3(__dp4a(w0, 0x00010C90u, 0u));
+			};
+			auto apply_tail = [&](uint32_t idx2) {
+				const uint32_t r = smem_u32(tail) + idx2 * 32u;
+				apply_row(lds128(r), lds32(r + 16u), s);
+			};
+			auto rem8 = [&](uint32_t wa, uint32_t wb) {
+				wa &= 0x0f0f0f0fu; wb &= 0x0f0f0f0fu;
+				apply3(__dp4a(wb, 0x010C9000u, 0u));
+				apply3(__dp4a(wb, 0x00000001u, __dp4a(wa, 0x0C900000u, 0u)));
+				apply_tail(__dp4a(wa, 0x0000010Du, 0u));
+			};
+			auto rem4 = [&](uint32_t wa) {
+				wa &= 0x0f0f0f0fu;
+				apply3(__dp4a(wa, 0x010C9000u, 0u));
+				apply_tail((wa & 0xffu) + 13u * 12u);
+			};
+			auto fold = [&]() { s.C0 = fold_twists(s.C0); s.C1 = fold_twists(s.C1); };
+			auto group24 = [&](int m) {
+				const uint32_t w0 = word_at(m), w1 = word_at(m + 4), w2 = word_at(m + 8), w3 = word_at(m + 12), w4 = word_at(m + 16), w5 = word_at(m + 20);
+				apply_words(w3, w4, w5); apply_words(w0, w1, w2);
+				fold();
+			};
+			const int M = depth - depth % 24;
+			int pos = depth;
+			if (pos > M) {
+				if (kWords) {
+					if (pos - 12 >= M) { apply_words(word_at(pos - 12), word_at(pos - 8), word_at(pos - 4)); pos -= 12; }
+					if (pos - 8 >= M) rem8(word_at(pos - 8), word_at(pos - 4));
+					else if (pos - 4 >= M) rem4(word_at(pos - 4));
+				} else {
+					for (; pos - 3 >= M; pos -= 3) apply3(inv_at(pos - 1) + 12u * inv_at(pos - 2) + 144u * inv_at(pos - 3));
+					if (pos > M) apply_tail(inv_at(pos - 1) + 13u * (pos - 2 >= M ? inv_at(pos - 2) : 12u));
+				}
+				fold();
+			}
+			for (int m = M - 24; m >= 0; m -= 24) group24(m);
+			cubie_major(s, res);
+		}
+		quad_sync(quad);                                                  // the whole tile is consumed
+		{
+			uint32_t* dst_row = reinterpret_cast<uint32_t*>(tile + my_cube * 20);   // results packed [cube][20] at the head of the tile
+#pragma unroll
+			for (int j = 0; j < 5; ++j) dst_row[j] = res[j];
+		}
+		quad_sync(quad);
+		uint32_t outw[5];
+#pragma unroll
+		for (int t = 0; t < 5; ++t) {
+			const int j = (int)tq + kSpan * t;
+			outw[t] = j < cnt * 5 ? tilew[j] : 0u;
+		}
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic reads / writes of the tile before its async refill
+		quad_sync(quad);
+		if (tq == 0) issue(span + stride);
+		uint8_t* dst = reinterpret_cast<uint8_t*>(out) + span * kSpan * out_pitch;
+		if (out_pitch == 20 && (reinterpret_cast<uintptr_t>(out) & 3u) == 0) {
+#pragma unroll
+			for (int t = 0; t < 5; ++t) {
+				const int j = (int)tq + kSpan * t;
+				if (j < cnt * 5) reinterpret_cast<uint32_t*>(dst)[j] = outw[t];
+			}
+		} else {
+#pragma unroll
+			for (int t = 0; t < 5; ++t) {
+				const int j = (int)tq + kSpan * t, c = j / 5, q = j - 5 * c;
+				if (j < cnt * 5) {
+					if ((reinterpret_cast<uintptr_t>(out) & 3u) == 0 && (out_pitch & 3) == 0) *reinterpret_cast<uint32_t*>(dst + c * out_pitch + 4 * q) = outw[t];
+					else
+						for (int b = 0; b < 4; ++b) dst[c * out_pitch + 4 * q + b] = (uint8_t)(outw[t] >> (8 * b));
+				}
+			}
+		}
+	}
+}
+
 static int env_int(const char* name, int dflt) {
 	const char* e = getenv(name);
 	return e ? atoi(e) : dflt;
@@ -722,8 +857,8 @@ static int ensure_device() {
 	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro3<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
 	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro3<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
 	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro3<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro3<0, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro3<1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+	RB_CUDA(cudaFuncSetAttribute(k_scramble_mm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+	RB_CUDA(cudaFuncSetAttribute(k_scramble_mm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
 	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
 	RB_CUDA(cudaFuncSetAttribute(k_scramble_macro<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
 	done[dev] = true;
@@ -745,11 +880,11 @@ static int warps_for(int64_t n, int depth) {
 // 3-move kernel: fixed shared memory and warps per CTA for a given depth (0: use the 2-move kernel)
 static int64_t fixed_smem3(int r2) { return (int64_t)kP1Bytes3 + (int64_t)kP2Rows3 * 4 * r2 + kTailBytes + kMaxThreads / 32 * 8; }
 constexpr int kStageThreads = 1024;             // threads that fill the table, whatever the number of working warps
-// row pitch of the action buffers (see the kernel): move-major tiles are padded to whole words, depth % 128 == 0 rows by 16 bytes
-static int pitch3(int depth, bool transposed = false) { return transposed ? (depth + 3) / 4 * 4 : (depth % 128 == 0 ? depth + 16 : depth); }
-static int warps_for3(int64_t n, int depth, int r2, bool transposed = false) {
+// row pitch of the action buffers (see the kernel): depth % 128 == 0 rows are padded by 16 bytes
+static int pitch3(int depth) { return depth % 128 == 0 ? depth + 16 : depth; }
+static int warps_for3(int64_t n, int depth, int r2) {
 	if (depth < 20) return 0;
-	int64_t w = (kSmemBudget - 16 - fixed_smem3(r2)) / (32 * (int64_t)pitch3(depth, transposed));
+	int64_t w = (kSmemBudget - 16 - fixed_smem3(r2)) / (32 * (int64_t)pitch3(depth));
 	if (w > max_threads() / 32) w = max_threads() / 32;
 	if (w < 8) return 0;                         // long sequences: too few resident warps to hide the table latency
 	const int64_t spread = ((n + 31) / 32 + RB_NUM_SMS - 1) / RB_NUM_SMS;
@@ -781,49 +916,68 @@ static int box_height(int depth) {
 
 // Can the move-major ([depth][n]) fast path take this call?
 static bool can_transposed(const uint8_t* actions, int64_t n, int depth) {
-	return depth >= 20 && n % 16 == 0 && (reinterpret_cast<uintptr_t>(actions) & 15u) == 0 && box_height(depth) > 0 && encode_tiled_fn() != nullptr;
+	return depth >= 20 && n % 16 == 0 && n < (int64_t(1) << 31) && (reinterpret_cast<uintptr_t>(actions) & 15u) == 0 && box_height(depth) > 0 &&
+	       encode_tiled_fn() != nullptr;
 }
 
-// actions: cube-major uint8 [n][depth], or move-major uint8 [depth][n] when `transposed` (see can_transposed)
-static int launch(const uint8_t* actions, int8_t* out, int64_t n, int depth, cudaStream_t st, int out_pitch = 20, bool transposed = false) {
+// quads (tiles of 128 cubes x depth bytes) per CTA for the move-major kernel; 0 = does not apply
+static int quads_for(int64_t n, int depth) {
+	if (depth < 20) return 0;
+	int64_t q = (kSmemBudget - 16 - fixed_smem3(1)) / ((int64_t)kSpan * depth);
+	if (q > kMaxThreads / 128) q = kMaxThreads / 128;
+	if (q < 2) return 0;
+	const int64_t spread = ((n + kSpan - 1) / kSpan + RB_NUM_SMS - 1) / RB_NUM_SMS;
+	if (q > spread) q = spread;
+	return (int)q;
+}
+
+// move-major actions uint8 [depth][n] (see can_transposed / quads_for)
+static int launch_mm(const uint8_t* actions, int8_t* out, int64_t n, int depth, cudaStream_t st, int out_pitch = 20) {
+	int rc = ensure_device();
+	if (rc != RB_OK) return rc;
+	const int Q = quads_for(n, depth), bh = box_height(depth);
+	if (Q <= 0 || bh <= 0) return rb_fail(RB_ERR_BAD_ARG, "move-major fast path does not apply%s%s");
+	CUtensorMap tmap;
+	const cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)depth}, gstride[1] = {(cuuint64_t)n};
+	const cuuint32_t box[2] = {(cuuint32_t)kSpan, (cuuint32_t)bh}, estride[2] = {1u, 1u};
+	const CUresult cr = encode_tiled_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(actions), gdim, gstride, box, estride,
+	                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+	                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (cr != CUDA_SUCCESS) return rb_fail(RB_ERR_CUDA, "cuTensorMapEncodeTiled failed for the move-major action array%s%s");
+	const int64_t spans = (n + kSpan - 1) / kSpan, ctas = (spans + Q - 1) / Q;
+	const int grid = (int)(ctas < RB_NUM_SMS ? ctas : RB_NUM_SMS);
+	size_t smem = (size_t)fixed_smem3(1) + (size_t)Q * kSpan * depth + 16;
+	if (smem < (size_t)kMinSmem3) smem = kMinSmem3;
+	if (depth % 4 == 0) k_scramble_mm<true><<<grid, kStageThreads, smem, st>>>(tmap, out, n, depth, out_pitch, 4u, (uint32_t)Q, bh);
+	else k_scramble_mm<false><<<grid, kStageThreads, smem, st>>>(tmap, out, n, depth, out_pitch, 4u, (uint32_t)Q, bh);
+	RB_LAUNCHED("scramble_mm_2024");
+	return RB_OK;
+}
+
+// actions: cube-major uint8 [n][depth]
+static int launch(const uint8_t* actions, int8_t* out, int64_t n, int depth, cudaStream_t st, int out_pitch = 20) {
 	int rc = ensure_device();
 	if (rc != RB_OK) return rc;
 	static const int rows_per = env_int("RB_SCRAMBLE_MOVES_PER_ROW", 3), r2_env = env_int("RB_SCRAMBLE_R2", 1);
-	const int r2 = (!transposed && depth % 4 == 0 && depth % 16 != 0 && (r2_env == 2 || r2_env == 4)) ? r2_env : 1;
-	const int W3 = rows_per == 3 || transposed ? warps_for3(n, depth, r2, transposed) : 0;
-	CUtensorMap tmap;
-	memset(&tmap, 0, sizeof(tmap));
+	const int r2 = (depth % 4 == 0 && depth % 16 != 0 && (r2_env == 2 || r2_env == 4)) ? r2_env : 1;
+	const int W3 = rows_per == 3 ? warps_for3(n, depth, r2) : 0;
 	if (W3 > 0) {
 		const int64_t ctas = ((n + 31) / 32 + W3 - 1) / W3;
 		const int grid = (int)(ctas < RB_NUM_SMS ? ctas : RB_NUM_SMS);
 		// the table is staged by a full CTA however few warps have work (4096 cubes: 128 single-warp CTAs took 70 us to fill it)
 		const int threads = W3 * 32 < kStageThreads ? kStageThreads : W3 * 32;
-		size_t smem = (size_t)fixed_smem3(r2) + (size_t)W3 * 32 * pitch3(depth, transposed) + 16;
+		size_t smem = (size_t)fixed_smem3(r2) + (size_t)W3 * 32 * pitch3(depth) + 16;
 		if (smem < (size_t)kMinSmem3) smem = kMinSmem3;
 		const uint32_t nw = (uint32_t)W3;
-		if (transposed) {
-			const int bh = box_height(depth);
-			const cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)depth}, gstride[1] = {(cuuint64_t)n};
-			const cuuint32_t box[2] = {32u, (cuuint32_t)bh}, estride[2] = {1u, 1u};
-			const CUresult cr = encode_tiled_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(actions), gdim, gstride, box, estride,
-			                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-			                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-			if (cr != CUDA_SUCCESS) return rb_fail(RB_ERR_CUDA, "cuTensorMapEncodeTiled failed for the move-major action array%s%s");
-			if (depth % 4 != 0) k_scramble_macro3<0, 1, true><<<grid, threads, smem, st>>>(actions, out, n, depth, out_pitch, 4u, nw, tmap, bh);
-			else k_scramble_macro3<1, 1, true><<<grid, threads, smem, st>>>(actions, out, n, depth, out_pitch, 4u, nw, tmap, bh);
-			RB_LAUNCHED("scramble_macro3t_2024");
-			return RB_OK;
-		}
-		if (depth % 4 != 0) k_scramble_macro3<0, 1><<<grid, threads, smem, st>>>(actions, out, n, depth, out_pitch, 4u, nw, tmap, 0);
-		else if (depth % 128 == 0) k_scramble_macro3<3, 1><<<grid, threads, smem, st>>>(actions, out, n, depth, out_pitch, 4u, nw, tmap, 0);
-		else if (depth % 16 == 0) k_scramble_macro3<2, 1><<<grid, threads, smem, st>>>(actions, out, n, depth, out_pitch, 4u, nw, tmap, 0);
-		else if (r2 == 2) k_scramble_macro3<1, 2><<<grid, threads, smem, st>>>(actions, out, n, depth, out_pitch, 8u, nw, tmap, 0);
-		else if (r2 == 4) k_scramble_macro3<1, 4><<<grid, threads, smem, st>>>(actions, out, n, depth, out_pitch, 16u, nw, tmap, 0);
-		else k_scramble_macro3<1, 1><<<grid, threads, smem, st>>>(actions, out, n, depth, out_pitch, 4u, nw, tmap, 0);
+		if (depth % 4 != 0) k_scramble_macro3<0, 1><<<grid, threads, smem, st>>>(actions, out, n, depth, out_pitch, 4u, nw);
+		else if (depth % 128 == 0) k_scramble_macro3<3, 1><<<grid, threads, smem, st>>>(actions, out, n, depth, out_pitch, 4u, nw);
+		else if (depth % 16 == 0) k_scramble_macro3<2, 1><<<grid, threads, smem, st>>>(actions, out, n, depth, out_pitch, 4u, nw);
+		else if (r2 == 2) k_scramble_macro3<1, 2><<<grid, threads, smem, st>>>(actions, out, n, depth, out_pitch, 8u, nw);
+		else if (r2 == 4) k_scramble_macro3<1, 4><<<grid, threads, smem, st>>>(actions, out, n, depth, out_pitch, 16u, nw);
+		else k_scramble_macro3<1, 1><<<grid, threads, smem, st>>>(actions, out, n, depth, out_pitch, 4u, nw);
 		RB_LAUNCHED("scramble_macro3_2024");
 		return RB_OK;
 	}
-	if (transposed) return rb_fail(RB_ERR_BAD_ARG, "move-major fast path does not apply%s%s");
 	const int W = warps_for(n, depth);
 	const int64_t ctas = ((n + 31) / 32 + W - 1) / W;
 	const int grid = (int)(ctas < RB_NUM_SMS ? ctas : RB_NUM_SMS);

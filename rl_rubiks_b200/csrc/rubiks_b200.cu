@@ -198,10 +198,9 @@ int rb_scramble(int rep, const uint8_t* actions, int64_t stride_cube, int64_t st
 			RB_LAUNCHED("compose_2024");
 			return RB_OK;
 		}
-		if (depth > 0 && stride_cube == 1 && stride_move == n && start != out && rbs::can_transposed(actions, n, depth) &&
-		    rbs::warps_for3(n, depth, 1, true) > 0) {
+		if (depth > 0 && stride_cube == 1 && stride_move == n && start != out && rbs::can_transposed(actions, n, depth) && rbs::quads_for(n, depth) > 0) {
 			// move-major actions [depth][n], the reference's draw shape (cube.py:226-227): 2-D tensor copies + in-register transposes
-			int rc = rbs::launch(actions, out, n, depth, S(stream), 20, true);
+			int rc = rbs::launch_mm(actions, out, n, depth, S(stream), 20);
 			if (rc != RB_OK || !start) return rc;
 			rb2024::k_compose<<<rb_grid(n, 8, 8), rb2024::kThreads, 0, S(stream)>>>(out, start, n);
 			RB_LAUNCHED("compose_2024");
@@ -223,8 +222,8 @@ int rb_scramble(int rep, const uint8_t* actions, int64_t stride_cube, int64_t st
 			return RB_OK;
 		}
 		if (depth > 0 && stride_cube == 1 && stride_move == n && start != out && rbt::host().stickers_ok && rbs::can_transposed(actions, n, depth) &&
-		    rbs::warps_for3(n, depth, 1, true) > 0) {
-			int rc = rbs::launch(actions, out, n, depth, S(stream), rb686::kStateBytes, true);
+		    rbs::quads_for(n, depth) > 0) {
+			int rc = rbs::launch_mm(actions, out, n, depth, S(stream), rb686::kStateBytes);
 			if (rc != RB_OK) return rc;
 			rb686::k_render_from2024<<<rb_grid((n + 31) / 32, rb686::kWarps, 8), rb686::kThreads, 0, S(stream)>>>(out, start, n);
 			RB_LAUNCHED("render_686");
