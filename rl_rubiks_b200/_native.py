@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librubiks_b200.so")
+LIB_PATH = os.environ.get("RB_LIB_PATH") or os.path.join(_HERE, "librubiks_b200.so")      # RB_LIB_PATH: kernel experiments (tools/)
 
 RB_OK, RB_ERR_BAD_ARG, RB_ERR_CUDA, RB_ERR_RANGE, RB_ERR_CAPACITY = 0, 1, 2, 3, 4
 REP_2024, REP_686 = 0, 1
