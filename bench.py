@@ -28,9 +28,9 @@ sys.path.insert(0, ROOT)
 N_CUBES = 1 << 24
 DEPTH = 100
 BYTES_PER_CUBE = DEPTH + 20          # uint8 actions in + int8[20] state out
-# dram__bytes_read.sum + dram__bytes_write.sum of one 2^24-cube launch, from the ncu --set full capture summarised in
-# profiles/r1q_scramble_macro3_ncu.txt (1.677844 GB + 0.322344 GB): the kernel moves exactly its algorithmic bytes.
-NCU_DRAM_BYTES_PER_CUBE = (1.677844e9 + 0.322344e9) / (1 << 24)
+# ncu --set full capture of the shipped scramble kernel (one 2^24-cube launch), summarised by tools/ncu_summary.py: bench.py reads
+# `roofline.traffic` (dram read + write) and the limiter percentages from this file at run time.
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r2_scramble_macro3_ncu.json")
 METRIC, UNIT = "cube_moves_per_sec", "moves/s"
 WORKLOAD = "raw scramble: 2^24 cubes x 100 random moves per GPU, 20x24 rep, packed int8 (BASELINE configs[1])"
 
@@ -40,6 +40,25 @@ def measured_peaks():
 	if os.path.exists(path):
 		return json.load(open(path)), "measured (MEASURED_PEAKS.json)"
 	return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def ncu_capture():
+	"""-> (dram bytes per cube, limiter dict, source) from the committed ncu summary, or (None, None, why)."""
+	try:
+		m = json.load(open(NCU_SUMMARY))["launches"][0]["metrics"]
+		per_cube = (m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"]) / (1 << 24)
+		lim = {"l1tex_pct": m["l1tex__throughput.avg.pct_of_peak_sustained_elapsed"],
+			   "alu_pipe_pct": m["sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"],
+			   "fma_pipe_pct": m["sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"],
+			   "issue_active_pct": m["smsp__issue_active.avg.pct_of_peak_sustained_active"],
+			   "dram_pct": m["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"],
+			   "shared_wavefronts": m["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"],
+			   "shared_bank_conflict_replays": m["l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"],
+			   "resource": "integer ALU + heavy-FMA issue at 8 warps per sub-partition (math_pipe_throttle / dispatch stalls); relieving l1tex "
+						   "(94 %) does not speed the kernel up: profiles/r2_scramble_pipe_experiments.txt"}
+		return per_cube, lim, "ncu --set full, " + os.path.relpath(NCU_SUMMARY, ROOT)
+	except (OSError, KeyError, IndexError, ValueError) as e:
+		return None, None, f"no ncu summary ({e})"
 
 
 class ClockSampler:
@@ -111,31 +130,51 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------------
-# CPU legs: the oracle port (numpy restatement of the reference's algorithm), fanned out over the host cores
+# CPU legs, fanned out over the host cores.  kind "reference": the reference's OWN librubiks.cube (unmodified copy under
+# baseline/_ref, made by baseline/make_ref.py; travels to the GPU box with the working tree) running the loop of cube.py:229-231,
+# `states = multi_rotate(states, faces[d], dirs[d])` for d in range(depth).  kind "port": the numpy oracle (the restatement used
+# as the parity checker), about 2.3 x faster per core than the reference because it looks moves up in one direct table.
 # ------------------------------------------------------------------------------------------------------------
-CPU_CHUNK = 1 << 14          # cubes per numpy call: the (n, depth) int64 draws of a chunk stay cache/RAM friendly
+CPU_CHUNK = 1 << 14          # cubes per numpy call: the (depth, n) int64 draws of a chunk stay cache/RAM friendly
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def ref_available() -> bool:
+	return os.path.exists(os.path.join(REF_DIR, "librubiks", "cube", "cube.py"))
 
 
 def _cpu_worker(args):
-	seed, chunks, depth = args
-	from oracle import cube_oracle as O
+	seed, chunks, depth, kind = args
 	g = np.random.RandomState(seed)
-	faces, dirs = g.randint(0, 6, (CPU_CHUNK, depth)), g.randint(0, 2, (CPU_CHUNK, depth))
+	faces, dirs = g.randint(0, 6, (depth, CPU_CHUNK)), g.randint(0, 2, (depth, CPU_CHUNK))
+	if kind == "reference":
+		if REF_DIR not in sys.path:
+			sys.path.insert(0, REF_DIR)
+		from librubiks import cube as ref_cube
+		ref_cube.set_is2024(True)
+		t0 = time.perf_counter()
+		for _ in range(chunks):
+			states = np.array([ref_cube.get_solved()] * CPU_CHUNK)
+			for d in range(depth):
+				states = ref_cube.multi_rotate(states, faces[d], dirs[d])
+		return time.perf_counter() - t0
+	from oracle import cube_oracle as O
+	faces, dirs = np.ascontiguousarray(faces.T), np.ascontiguousarray(dirs.T)
 	t0 = time.perf_counter()
 	for _ in range(chunks):
 		O.scramble_many(faces, dirs, True)
 	return time.perf_counter() - t0
 
 
-def cpu_scramble_throughput(chunks_per_core: int, depth: int, cores: int, pool=None):
-	"""moves/s of the numpy port: `cores` processes, each scrambling `chunks_per_core` x 2^14 cubes (wall clock of the slowest)."""
+def cpu_scramble_throughput(chunks_per_core: int, depth: int, cores: int, kind: str, pool=None):
+	"""moves/s of the CPU path: `cores` processes, each scrambling `chunks_per_core` x 2^14 cubes (wall clock of the slowest)."""
 	import multiprocessing as mp
 	own = pool is None
 	if own:
 		pool = mp.get_context("fork").Pool(cores)
 	try:
 		t0 = time.perf_counter()
-		pool.map(_cpu_worker, [(s, chunks_per_core, depth) for s in range(cores)])
+		pool.map(_cpu_worker, [(s, chunks_per_core, depth, kind) for s in range(cores)])
 		dt = time.perf_counter() - t0
 	finally:
 		if own:
@@ -143,32 +182,39 @@ def cpu_scramble_throughput(chunks_per_core: int, depth: int, cores: int, pool=N
 	return cores * chunks_per_core * CPU_CHUNK * depth / dt, dt
 
 
+def cpu_sample_text(kind, cores, chunks, depth, dt=None):
+	what = ("the reference's own librubiks.cube.multi_rotate loop (cube.py:229-231, unmodified copy in baseline/_ref)" if kind == "reference"
+			else "numpy oracle port of cube.py:206-263")
+	return f"{cores} processes x {chunks * CPU_CHUNK} cubes x {depth} moves, {what}" + (f", {dt:.1f} s" if dt is not None else "") + \
+		"; throughput per move, the GPU arm runs 2^24 cubes"
+
+
 def run_reference(args):
-	"""--impl reference: the reference's numpy algorithm for this path (oracle port; the reference is pure Python and
-	cannot travel to the GPU box) on all host cores, bounded sample per step."""
+	"""--impl reference: the reference's CPU implementation of the path on all host cores, a bounded sample per step."""
 	rank = int(os.environ.get("RANK", "0"))
 	if rank != 0:
 		return
 	import multiprocessing as mp
 	cores = os.cpu_count() or 1
-	per_core = 4                                          # chunks of 2^14 cubes per core and step: ~1 s of CPU work per step
+	kind = "reference" if ref_available() else "port"
+	per_core = 2 if kind == "reference" else 4            # chunks of 2^14 cubes per core and step: ~1.3 s of CPU work per step
 	pool = mp.get_context("fork").Pool(cores)
 	try:
 		for _ in range(args.warmup):
-			cpu_scramble_throughput(per_core, DEPTH, cores, pool)
+			cpu_scramble_throughput(per_core, DEPTH, cores, kind, pool)
 		t0 = time.perf_counter()
 		for _ in range(args.steps):
-			cpu_scramble_throughput(per_core, DEPTH, cores, pool)
+			cpu_scramble_throughput(per_core, DEPTH, cores, kind, pool)
 		dt = time.perf_counter() - t0
 	finally:
 		pool.close()
 	value = args.steps * cores * per_core * CPU_CHUNK * DEPTH / dt
-	sample = f"{cores} processes x {per_core * CPU_CHUNK} cubes x {DEPTH} moves per step (numpy oracle port of cube.py:206-263), extrapolated per move"
+	sample = cpu_sample_text(kind, cores, per_core, DEPTH) + " per step"
 	print(json.dumps({
 		"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
 		"warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
 		"vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
-		"cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+		"cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
 		"e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
 	}), flush=True)
 
@@ -306,7 +352,15 @@ def run_gpu(args):
 		a.record(); gadi.generate(); gadi.targets(values, 0.3); b.record()
 		torch.cuda.synchronize()
 		adi_ms.append(a.elapsed_time(b))
-	adi_t = float(np.median(adi_ms)) * 1e-3
+	def over_ranks(seconds):
+		"""(max over ranks, this rank's): every rank generates its own batch, the aggregate rate is world * batch / slowest rank."""
+		t = torch.tensor([seconds], dtype=torch.float64, device=dev)
+		if world > 1:
+			dist.all_reduce(t, op=dist.ReduceOp.MAX)
+		return float(t.item())
+
+	adi_t_rank = float(np.median(adi_ms)) * 1e-3
+	adi_t = over_ranks(adi_t_rank)
 	nst = games * adepth
 	# same batch with bf16 one-hot rows (opt-in dtype, not the reference's: half the write traffic, input of a bf16 forward)
 	gadi16 = adi.ADIGenerator(games, adepth, "lapanfix", keep_states=True, oh_dtype=torch.bfloat16)
@@ -320,7 +374,7 @@ def run_gpu(args):
 		a.record(); gadi16.generate(); gadi16.targets(values, 0.3); b.record()
 		torch.cuda.synchronize()
 		adi16_ms.append(a.elapsed_time(b))
-	adi16_t = float(np.median(adi16_ms)) * 1e-3
+	adi16_t = over_ranks(float(np.median(adi16_ms)) * 1e-3)
 	adi16_bytes = 960 * 13 * nst + 20 * nst + 13 * nst + 4 * 12 * nst + 16 * nst + nst
 	adi_bytes = 1920 * 13 * nst + 20 * nst + 13 * nst + 4 * 12 * nst + 16 * nst + nst      # 626 450 000 B
 
@@ -333,23 +387,26 @@ def run_gpu(args):
 			dist.destroy_process_group()
 		return
 	cores = os.cpu_count() or 1
-	cpu_chunks = 32                                        # ~10 s of work on every host core
-	cpu_value, cpu_dt = cpu_scramble_throughput(cpu_chunks, depth, cores)
+	cpu_kind = "reference" if ref_available() else "port"
+	cpu_chunks = 12 if cpu_kind == "reference" else 32     # ~8-10 s of work on every host core
+	cpu_value, cpu_dt = cpu_scramble_throughput(cpu_chunks, depth, cores, cpu_kind)
+	port_value, port_dt = cpu_scramble_throughput(16, depth, cores, "port")
+	ncu_per_cube, limiter, ncu_src = ncu_capture()
 	result = {
 		"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
 		"ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
 		"data": "synthetic",
 		"config": {"workload": WORKLOAD, "cubes_per_gpu": n, "depth": depth, "actions": "host-supplied uint8 [n][100], resident in HBM",
 				   "l2": "inputs (1.68 GB actions) larger than the 126 MB L2, no reuse between steps", "parity_subsample_ok": parity_ok},
-		"roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": int(NCU_DRAM_BYTES_PER_CUBE * n),
-					 "traffic_source": "ncu --set full, profiles/r1q_scramble_macro3_ncu.txt (dram read + write per launch, scaled by cubes)",
-					 "peak_source": peak_src, "kernel": "rbs::k_scramble_macro3<true, 1>", "kernel_ms": kernel_ms,
+		"roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+					 "traffic": int(ncu_per_cube * n) if ncu_per_cube is not None else None,
+					 "traffic_source": ncu_src + " (dram read + write of one 2^24-cube launch, scaled by cubes)",
+					 "peak_source": peak_src, "kernel": "rbs::k_scramble_macro3<1, 1>", "kernel_ms": kernel_ms,
 					 "algorithmic_bytes_per_launch": BYTES_PER_CUBE * n,
-					 "note": "multi-move scramble is bound by shared-memory table wavefronts (l1tex 94 %) and the integer ALU pipe (66 %), not HBM: see DESIGN.md 3.1",
-					 "limiter": {"resource": "shared-memory wavefronts (l1tex)", "pct_of_peak": 94.2, "alu_pipe_pct": 65.8, "dram_pct": 28.7,
-								 "source": "ncu --set full, profiles/r1q_scramble_macro3_ncu.txt"}},
-		"cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
-						 "sample": f"{cores} processes x {cpu_chunks * CPU_CHUNK} cubes x {depth} moves, numpy oracle port, {cpu_dt:.1f} s"},
+					 "note": "100 dependent moves per 120 bytes: the multi-move scramble is instruction-bound (integer ALU + heavy-FMA issue), not HBM-bound: DESIGN.md 3.1",
+					 "limiter": dict(limiter, source=ncu_src) if limiter else None},
+		"cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": cpu_kind, "sample": cpu_sample_text(cpu_kind, cores, cpu_chunks, depth, cpu_dt),
+						 "port": {"value": port_value, "kind": "port", "sample": cpu_sample_text("port", cores, 16, depth, port_dt)}},
 		"e2e": {"value": world * n * depth / seeded_s, "unit": UNIT, "h2d_bytes_per_step": 16, "d2h_bytes_per_step": n * 20,
 				"ms_per_step": seeded_s * 1e3, "parity_ok": seeded_ok,
 				"api": "rbh_scramble_seeded (C ABI): the moves are drawn on the device (Philox4x32-10, one subsequence per cube) as cube.scramble "
@@ -363,15 +420,17 @@ def run_gpu(args):
 								   "algorithmic_bytes_per_cube": 70}},
 		"gpu_launches": int(launches),
 		"clocks": clocks.summary(),
-		"extra": {"seeded_kernel": {"workload": "rb_scramble_seeded, device-resident: Philox draw + scramble in one kernel, 20 B per cube written",
+		"extra": {"note": "adi / adi_bf16_rows: every rank generates its own batch (weak scaling); samples_per_sec = n_gpus x batch / slowest rank",
+				  "seeded_kernel": {"workload": "rb_scramble_seeded, device-resident: Philox draw + scramble in one kernel, 20 B per cube written",
 									"moves_per_sec": world * n * depth / (seeded_kernel_ms * 1e-3), "ms": seeded_kernel_ms},
 				  "adi": {"workload": "fused ADI batch 1000 games x depth 25 (BASELINE configs[0]): generate + targets kernels",
-						  "samples_per_sec": nst / adi_t, "children_per_sec": 12 * nst / adi_t, "ms": adi_t * 1e3,
+						  "samples_per_sec": world * nst / adi_t, "children_per_sec": world * 12 * nst / adi_t, "ms": adi_t * 1e3,
+							  "samples_per_sec_per_gpu": nst / adi_t, "n_gpus": world,
 						  "roofline": {"bound": "hbm", "achieved": adi_bytes / adi_t / 1e9, "peak": peak, "unit": "GB/s",
 									   "frac": adi_bytes / adi_t / 1e9 / peak, "algorithmic_bytes": adi_bytes},
 						  "l2": "256 MB flush buffer written between timed iterations"},
 				  "adi_bf16_rows": {"workload": "same batch, one-hot rows emitted as bfloat16 (opt-in; the reference's dtype is f32)",
-									"samples_per_sec": nst / adi16_t, "ms": adi16_t * 1e3,
+									"samples_per_sec": world * nst / adi16_t, "samples_per_sec_per_gpu": nst / adi16_t, "ms": adi16_t * 1e3,
 									"roofline": {"bound": "hbm", "achieved": adi16_bytes / adi16_t / 1e9, "peak": peak, "unit": "GB/s",
 												 "frac": adi16_bytes / adi16_t / 1e9 / peak, "algorithmic_bytes": adi16_bytes}}},
 	}
