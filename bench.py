@@ -145,6 +145,7 @@ def ref_available() -> bool:
 
 def _cpu_worker(args):
 	seed, chunks, depth, kind = args
+	os.environ["CUDA_VISIBLE_DEVICES"] = ""          # CPU legs: the reference picks its device at import time (librubiks/__init__.py:5-6)
 	g = np.random.RandomState(seed)
 	faces, dirs = g.randint(0, 6, (depth, CPU_CHUNK)), g.randint(0, 2, (depth, CPU_CHUNK))
 	if kind == "reference":
@@ -168,18 +169,26 @@ def _cpu_worker(args):
 
 def cpu_scramble_throughput(chunks_per_core: int, depth: int, cores: int, kind: str, pool=None):
 	"""moves/s of the CPU path: `cores` processes, each scrambling `chunks_per_core` x 2^14 cubes (wall clock of the slowest)."""
-	import multiprocessing as mp
 	own = pool is None
 	if own:
-		pool = mp.get_context("fork").Pool(cores)
+		pool = cpu_pool(cores, depth, kind)
 	try:
 		t0 = time.perf_counter()
-		pool.map(_cpu_worker, [(s, chunks_per_core, depth, kind) for s in range(cores)])
+		pool.map(_cpu_worker, [(s, chunks_per_core, depth, kind) for s in range(cores)], chunksize=1)
 		dt = time.perf_counter() - t0
 	finally:
 		if own:
 			pool.close()
 	return cores * chunks_per_core * CPU_CHUNK * depth / dt, dt
+
+
+def cpu_pool(cores: int, depth: int, kind: str):
+	"""Worker processes started with `spawn` (the parent may hold a CUDA context, which a forked child must not touch) and warmed
+	up: every worker has imported numpy / torch / the CPU implementation before anything is timed."""
+	import multiprocessing as mp
+	pool = mp.get_context("spawn").Pool(cores)
+	pool.map(_cpu_worker, [(s, 0, depth, kind) for s in range(4 * cores)], chunksize=1)
+	return pool
 
 
 def cpu_sample_text(kind, cores, chunks, depth, dt=None):
@@ -194,11 +203,10 @@ def run_reference(args):
 	rank = int(os.environ.get("RANK", "0"))
 	if rank != 0:
 		return
-	import multiprocessing as mp
 	cores = os.cpu_count() or 1
 	kind = "reference" if ref_available() else "port"
 	per_core = 2 if kind == "reference" else 4            # chunks of 2^14 cubes per core and step: ~1.3 s of CPU work per step
-	pool = mp.get_context("fork").Pool(cores)
+	pool = cpu_pool(cores, DEPTH, kind)
 	try:
 		for _ in range(args.warmup):
 			cpu_scramble_throughput(per_core, DEPTH, cores, kind, pool)
