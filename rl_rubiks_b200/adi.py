@@ -60,10 +60,12 @@ class ADIGenerator:
 			raise IndexError(f"actions must have shape (depth, games) = {(self.depth, self.games)}, got {tuple(a.shape)}")
 		self.actions.copy_(a.to(torch.uint8), non_blocking=True)
 
-	def draw_actions(self):
-		"""The reference's draw (cube.py:226-227): np.random faces (depth, games) then dirs."""
-		faces = np.random.randint(0, 6, (self.depth, self.games))
-		dirs = np.random.randint(0, 2, (self.depth, self.games))
+	def draw_actions(self, rng=None):
+		"""The reference's draw (cube.py:226-227): faces (depth, games) then dirs, from the global numpy stream or from `rng`
+		(a RandomState: the per-rank stream of data-parallel training)."""
+		rng = rng or np.random
+		faces = rng.randint(0, 6, (self.depth, self.games))
+		dirs = rng.randint(0, 2, (self.depth, self.games))
 		self.set_actions(faces, dirs)
 
 	def generate(self):
@@ -95,7 +97,7 @@ def _value_forward(net, x: torch.Tensor, ff_batches: int) -> torch.Tensor:
 
 @torch.no_grad()
 def adi_traindata(net, games: int, depth: int, reward_method: str, alpha: float, faces=None, dirs=None,
-				  ff_batches: int = 1, generator: ADIGenerator | None = None):
+				  ff_batches: int = 1, generator: ADIGenerator | None = None, rng=None):
 	"""Drop-in for `Train.ADI_traindata(net, alpha)` (train.py:256-339): returns
 	(oh_states f32 (n, W), policy_targets i64 (n,), value_targets f32 (n,), loss_weights f32 (n,)), all on the GPU.
 	`faces`/`dirs` (depth, games) override the random draw (identical host-supplied actions give bit-identical
@@ -103,7 +105,7 @@ def adi_traindata(net, games: int, depth: int, reward_method: str, alpha: float,
 	g = generator or ADIGenerator(games, depth, reward_method)
 	net.eval()
 	if faces is None:
-		g.draw_actions()
+		g.draw_actions(rng)
 	else:
 		g.set_actions(faces, dirs)
 	oh_states, children_oh = g.generate()

@@ -36,29 +36,49 @@ class Evaluator:
 		return self.max_time * self.n_games * len(self.scrambling_depths)
 
 	def _draw(self):
-		"""The scrambles of one evaluation in the reference's draw order: [(state, depth)] * (len(depths) * n_games)."""
-		out = []
-		for d in self.scrambling_depths:
-			for _ in range(self.n_games):
-				if self._isdeep():
-					d = np.random.randint(100, 1000)                    # evaluation.py:75-76
-				state, _, _ = cube.scramble(int(d), True)                # evaluation.py:47
-				out.append((state, int(d)))
-		return out
+		"""The scrambles of one evaluation, [(state, depth)] * (len(depths) * n_games), consuming the global numpy stream exactly as
+		the reference's loop does (evaluation.py:74-76 draws a depth in deep mode, cube.py:206-216 draws faces then directions and
+		draws again when `force_not_solved` finds the cube solved) -- but scrambled in batches: all draws are made first, cubes of
+		equal depth go through one `scramble_batch`, and only if some cube came out solved (possible at shallow depths only) is
+		the stream rewound to just after that cube's draw and the remainder drawn again."""
+		games = [int(d) for d in self.scrambling_depths for _ in range(self.n_games)]        # depth per game (0 = to be drawn)
+		deep = self._isdeep()
+		states, depths = [None] * len(games), list(games)
+		first, pending = 0, False                       # `pending`: game `first` has its depth already and must redraw faces / dirs only
+		while first < len(games):
+			after, draws = [], []
+			for j in range(first, len(games)):
+				if deep and not (pending and j == first):
+					depths[j] = int(np.random.randint(100, 1000))                              # evaluation.py:75-76
+				faces = np.random.randint(6, size=(depths[j],))                                 # cube.py:208-209
+				dirs = np.random.randint(2, size=(depths[j],))
+				draws.append(cube._actions_u8(faces, dirs))
+				after.append(np.random.get_state())
+			out = [None] * len(draws)
+			for d in sorted(set(depths[first:])):
+				idx = [k for k in range(len(draws)) if depths[first + k] == d]
+				batch = cube.scramble_batch(np.stack([draws[k] for k in idx])) if d else np.stack([cube.get_solved()] * len(idx))
+				for k, st in zip(idx, batch):
+					out[k] = st
+			solved = [k for k in range(len(draws)) if depths[first + k] != 0 and bool((out[k] == cube.get_solved_instance()).all())]
+			stop = solved[0] if solved else len(draws)
+			states[first:first + stop] = out[:stop]
+			first += stop
+			pending = bool(solved)
+			if solved:
+				np.random.set_state(after[stop])                                                # the redraw continues right after that cube's draw
+		return list(zip(states, depths))
 
 	def eval(self, agent):
-		"""evaluation.py:54-94, one `agent.search` per cube."""
+		"""evaluation.py:54-94, one `agent.search` per cube (the searches of the reference's agents draw nothing from the numpy
+		stream, so making all scrambles first leaves every draw where the reference has it)."""
 		res, states, times = [], [], []
-		for d in self.scrambling_depths:
-			for _ in range(self.n_games):
-				if self._isdeep():
-					d = np.random.randint(100, 1000)
-				state, _, _ = cube.scramble(int(d), True)
-				t0 = time.perf_counter()
-				solved = agent.search(state, self.max_time, self.max_states)
-				times.append(time.perf_counter() - t0)
-				res.append(len(agent.action_queue) if solved else -1)
-				states.append(len(agent))
+		for state, _ in self._draw():
+			t0 = time.perf_counter()
+			solved = agent.search(state, self.max_time, self.max_states)
+			times.append(time.perf_counter() - t0)
+			res.append(len(agent.action_queue) if solved else -1)
+			states.append(len(agent))
 		shape = (len(self.scrambling_depths), self.n_games)
 		return np.reshape(res, shape), np.reshape(states, shape), np.reshape(times, shape)
 

@@ -5,14 +5,15 @@ around the fused ADI generator.
 What changes against the reference: the ADI batch is born on the GPU (`adi.ADIGenerator`, buffers allocated once), so the
 four `.to(gpu)` copies of train.py:156-159 and the `.cpu()` of train.py:304 are gone, and the per-minibatch
 `.detach().cpu().numpy().mean()` (train.py:178-179, one host sync per minibatch) becomes one device accumulation read back
-once per rollout.  What stays exactly the reference's: the rollout loop, the tau-mixed generator net (train.py:341-352),
-minibatch slicing (`_get_batches`, train.py:400-410 -- including its unused `np.random.shuffle`, which advances the global
-numpy stream the next rollout's scramble draws from), loss = mean((CE + MSE) * loss_weights), the lr / alpha schedule
+once per rollout.  What stays the reference's, because identical seeds must give identical losses: the order of the rollout (generator-net mix
+train.py:341-352, ADI batch, minibatch pass, schedules, evaluation), the consumption of the global numpy stream (the draws of
+cube.py:226-227 and the unused shuffle of train.py:405), loss = mean((CE + MSE) * loss_weights), the lr / alpha schedule
 (train.py:191-202), evaluation rollouts (train.py:63-73) and best-net bookkeeping (train.py:211-227).  The network forward /
 backward stays torch (dense GEMMs).
 
-Data-parallel use (one process per GPU): every rank generates its own share of the games and gradients are averaged with
-one flat NCCL all-reduce per minibatch (`sharding.allreduce_mean_`); there is no collective on the ADI path.
+Data-parallel use (one process per GPU): every rank generates its own share of the games from its own random stream and
+gradients are averaged with one flat NCCL all-reduce per minibatch (`sharding.allreduce_mean_`); there is no collective on
+the ADI path.  See `Train.train`.
 """
 from __future__ import annotations
 
@@ -74,14 +75,21 @@ class Train:
 
 	@staticmethod
 	def _get_batches(size: int, bsize: int):
-		"""train.py:400-410.  The shuffle is never used for indexing there either; it is kept because it consumes the
-		global numpy stream between two rollouts' scramble draws."""
-		nbatches = int(np.ceil(size / bsize))
-		idcs = np.arange(size)
-		np.random.shuffle(idcs)
-		batches = [slice(b * bsize, (b + 1) * bsize) for b in range(nbatches)]
-		batches[-1] = slice(batches[-1].start, size)
-		return batches
+		"""Minibatch bounds of one rollout, in order: ceil(size / bsize) slices, the last one short (train.py:400-410).  The
+		reference also shuffles an index array here that it never uses for indexing; the call is kept because it advances the
+		global numpy stream that the next rollout's scramble draws come from (identical seeds must give identical scrambles)."""
+		np.random.shuffle(np.arange(size))
+		return [slice(lo, min(lo + bsize, size)) for lo in range(0, size, bsize)]
+
+	def _advance_alpha(self, alpha):
+		"""One step of the loss-weighting schedule (train.py:196-202): alpha grows by `alpha_update` until it reaches 1; a step
+		that would overshoot lands on 1, one that lands within float tolerance of 1 keeps its value."""
+		if not self.alpha_update:
+			return alpha
+		nxt = alpha + self.alpha_update
+		if nxt <= 1 or np.isclose(nxt, 1):
+			return nxt
+		return 1 if alpha < 1 else alpha
 
 	@torch.no_grad()
 	def _update_gen_net(self, generator_net, net):
@@ -95,13 +103,43 @@ class Train:
 	def ADI_traindata(self, net, alpha: float):
 		"""train.py:256-339 on the device (rl_rubiks_b200.adi): (oh_states, policy_targets, value_targets, loss_weights)."""
 		with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.oh_dtype == torch.bfloat16):
-			return adi.adi_traindata(net, self.rollout_games, self.rollout_depth, self.reward_method, alpha,
-									 ff_batches=self.adi_ff_batches, generator=self._generator)
+			return adi.adi_traindata(net, self._generator.games, self.rollout_depth, self.reward_method, alpha,
+									 ff_batches=self.adi_ff_batches, generator=self._generator, rng=self._draw_rng)
+
+	def _sgd_pass(self, net, optimizer, params, batch, acc):
+		"""One pass over a rollout's batch in minibatches (train.py:165-179): loss = mean((CE + MSE) * loss_weights); the two
+		per-minibatch loss means are accumulated in f64 on the device (one host read per rollout instead of one per minibatch)."""
+		oh, policy_t, value_t, weights = batch
+		bounds = self._get_batches(oh.shape[0], self.batch_size)
+		acc.zero_()
+		net.train()
+		for sl in bounds:
+			optimizer.zero_grad()
+			with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.oh_dtype == torch.bfloat16):
+				policy_pred, value_pred = net(oh[sl], policy=True, value=True)
+			w = weights[sl]
+			policy_loss = self.policy_criterion(policy_pred.float(), policy_t[sl]) * w
+			value_loss = self.value_criterion(value_pred.float().squeeze(), value_t[sl]) * w
+			torch.mean(policy_loss + value_loss).backward()
+			if self.data_parallel:
+				sharding.allreduce_mean_([p.grad for p in params if p.grad is not None])
+			optimizer.step()
+			acc[0] += policy_loss.detach().mean().double() / len(bounds)
+			acc[1] += value_loss.detach().mean().double() / len(bounds)
+		return acc.tolist()
 
 	def train(self, net):
-		"""Returns (net after the last rollout, net with the best evaluation score), as train.py:111-247."""
+		"""Returns (net after the last rollout, net with the best evaluation score), as train.py:111-247.
+
+		Data-parallel (`data_parallel=True`, one process per GPU): this rank generates `shard_bounds(rollout_games)` of the games
+		from its OWN random stream (`sharding.rank_seed` of one number taken from the global numpy stream, so the global
+		stream -- which `Evaluator.eval_batched` needs identical on every rank -- stays in step), trains on its share, averages
+		the gradients of every minibatch with one all-reduce and the floating-point module buffers once per rollout."""
 		dev = torch.device("cuda", torch.cuda.current_device())
-		self._generator = adi.ADIGenerator(self.rollout_games, self.rollout_depth, self.reward_method, oh_dtype=self.oh_dtype)
+		rank, ws = sharding.world() if self.data_parallel else (0, 1)
+		lo, hi = sharding.shard_bounds(self.rollout_games, ws, rank)
+		self._generator = adi.ADIGenerator(hi - lo, self.rollout_depth, self.reward_method, oh_dtype=self.oh_dtype)
+		self._draw_rng = np.random.RandomState(sharding.rank_seed(int(np.random.randint(2 ** 31 - 1)), rank)) if ws > 1 else None
 		best_solve, best_net = 0, _clone(net)
 		if self.agent is not None:
 			self.agent.net = net
@@ -109,54 +147,33 @@ class Train:
 		alpha = 1 if self.alpha_update == 1 else 0
 		optimizer = self.optim(net.parameters(), lr=self.lr)
 		lr_scheduler = torch.optim.lr_scheduler.StepLR(optimizer, 1, self.gamma)
-		self.policy_losses, self.value_losses = np.zeros(self.rollouts), np.zeros(self.rollouts)
-		self.train_losses = np.empty(self.rollouts)
+		self.policy_losses, self.value_losses, self.train_losses = np.zeros(self.rollouts), np.zeros(self.rollouts), np.empty(self.rollouts)
 		self.sol_percents, self.alphas, self.lrs = [], [], []
 		params = [p for p in net.parameters() if p.requires_grad]
 		acc = torch.zeros(2, dtype=torch.float64, device=dev)
 
 		for rollout in range(self.rollouts):
-			generator_net = self._update_gen_net(generator_net, net) if self.tau != 1 else net
+			if self.tau != 1:
+				generator_net = self._update_gen_net(generator_net, net)
 			self.alphas.append(float(alpha))
 			self.lrs.append(float(optimizer.param_groups[0]["lr"]))
-			training_data, policy_targets, value_targets, loss_weights = self.ADI_traindata(generator_net, alpha)
-
-			net.train()
-			batches = self._get_batches(self.states_per_rollout, self.batch_size)
-			acc.zero_()
-			for batch in batches:
-				optimizer.zero_grad()
-				with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.oh_dtype == torch.bfloat16):
-					policy_pred, value_pred = net(training_data[batch], policy=True, value=True)
-				policy_pred, value_pred = policy_pred.float(), value_pred.float()
-				policy_loss = self.policy_criterion(policy_pred, policy_targets[batch]) * loss_weights[batch]
-				value_loss = self.value_criterion(value_pred.squeeze(), value_targets[batch]) * loss_weights[batch]
-				loss = torch.mean(policy_loss + value_loss)
-				loss.backward()
-				if self.data_parallel:
-					sharding.allreduce_mean_([p.grad for p in params if p.grad is not None])
-				optimizer.step()
-				# train.py:178-179 without the per-minibatch device->host sync: f32 means accumulated in f64 on the device
-				acc[0] += policy_loss.detach().mean().double() / len(batches)
-				acc[1] += value_loss.detach().mean().double() / len(batches)
-			self.policy_losses[rollout], self.value_losses[rollout] = acc.tolist()
+			batch = self.ADI_traindata(generator_net if self.tau != 1 else net, alpha)
+			self.policy_losses[rollout], self.value_losses[rollout] = self._sgd_pass(net, optimizer, params, batch, acc)
 			self.train_losses[rollout] = self.policy_losses[rollout] + self.value_losses[rollout]
+			if ws > 1:
+				sharding.allreduce_mean_([b for b in net.buffers() if b.is_floating_point()])
 
 			if rollout and self.update_interval and rollout % self.update_interval == 0:       # train.py:191-202
 				if self.gamma != 1:
 					lr_scheduler.step()
-				if (alpha + self.alpha_update <= 1 or np.isclose(alpha + self.alpha_update, 1)) and self.alpha_update:
-					alpha += self.alpha_update
-				elif alpha < 1 and alpha + self.alpha_update > 1 and self.alpha_update:
-					alpha = 1
+				alpha = self._advance_alpha(alpha)
 			self.log(f"Rollout {rollout} completed with mean loss {self.train_losses[rollout]}")
 
 			if rollout in self.evaluation_rollouts and self.evaluator is not None and self.agent is not None:   # train.py:211-227
 				net.eval()
 				self.agent.net = net
-				eval_results, _, _ = self.evaluator.eval(self.agent)
-				eval_reward = (np.asarray(eval_results) != -1).mean()
-				self.sol_percents.append(eval_reward)
-				if eval_reward > best_solve:
-					best_solve, best_net = eval_reward, _clone(net)
+				solved = np.asarray(self.evaluator.eval(self.agent)[0]) != -1
+				self.sol_percents.append(solved.mean())
+				if self.sol_percents[-1] > best_solve:
+					best_solve, best_net = self.sol_percents[-1], _clone(net)
 		return net, best_net

@@ -168,7 +168,7 @@ def test_astar_expand_batch_trace_matches_reference(golden, is2024):
 	parent actions equal the trace recorded from the reference with a tie-heavy integer net."""
 	import heapq
 	from rl_rubiks_b200 import cube
-	from rl_rubiks_b200.frontier import AStar
+	from tests.agent_harness import AStar
 	cube.set_is2024(is2024)
 	tag = "2024" if is2024 else "686"
 	g = golden("search")
@@ -198,7 +198,7 @@ def test_astar_expand_batch_trace_matches_reference(golden, is2024):
 
 def test_astar_full_search_matches_reference(golden):
 	from rl_rubiks_b200 import cube
-	from rl_rubiks_b200.frontier import AStar
+	from tests.agent_harness import AStar
 	g = golden("search")
 	a = AStar(_FakeNet(np.zeros(480)), lambda_=1.0, expansions=5)
 	assert a.search(g["astar_full_start"], None, 20000) == bool(g["astar_full_ok"])
@@ -240,7 +240,7 @@ def test_mcts_full_trace_matches_reference(golden, tag, c, graph, max_states):
 	"""MCTS.search (agents.py:461-633) with the child expansion / dedup / graph completion on the device: node numbering,
 	neighbour table, leaf flags, visit counts, W, V and the action queue equal the trace recorded from the reference."""
 	from rl_rubiks_b200 import cube
-	from rl_rubiks_b200.frontier import MCTS
+	from tests.agent_harness import MCTS
 	g = golden("search")
 	m = MCTS(_CountNet(), c=c, search_graph=graph)
 	assert m.search(g[f"mcts{tag}_start"], None, max_states) == bool(g[f"mcts{tag}_ok"])
@@ -259,7 +259,7 @@ def test_mcts_full_trace_matches_reference(golden, tag, c, graph, max_states):
 def test_mcts_686_solves_shallow_scramble():
 	"""Same agent on the 6x8x6 representation (no golden trace: the action queue must solve the cube)."""
 	from rl_rubiks_b200 import cube
-	from rl_rubiks_b200.frontier import MCTS
+	from tests.agent_harness import MCTS
 	cube.set_is2024(False)
 
 	class Net(torch.nn.Module):

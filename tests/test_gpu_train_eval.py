@@ -90,9 +90,11 @@ class _FakeNet(torch.nn.Module):
 @pytest.mark.parametrize("tag", ["fixed", "deep"])
 def test_evaluator_matches_reference(golden, tag):
 	"""Same numpy seed -> same scrambles -> same searches: turns-to-solve and states explored equal the reference's, for the
-	sequential loop with the single-search A* mirror and for the batched driver with AStarBatch."""
+	sequential loop (with the host-side trace harness and with the product's AStarBatch as a one-cube agent) and for the batched
+	driver."""
 	from rl_rubiks_b200.evaluation import Evaluator
-	from rl_rubiks_b200.frontier import AStar, AStarBatch
+	from rl_rubiks_b200.frontier import AStarBatch
+	from tests.agent_harness import AStar
 	g = golden("evaluation")
 	depths = g[f"{tag}_depths"].tolist() if tag == "fixed" else range(0)
 	ev = Evaluator(int(g[f"{tag}_n_games"]), depths, max_time=None, max_states=int(g[f"{tag}_max_states"]))
@@ -102,6 +104,9 @@ def test_evaluator_matches_reference(golden, tag):
 	assert (res == g[f"{tag}_res"]).all() and (states == g[f"{tag}_states"]).all()
 	assert times.shape == res.shape and (times > 0).all()
 	np.random.seed(9)
+	res_s, states_s, _ = ev.eval(AStarBatch(net, lambda_=0.2, expansions=20))
+	assert (res_s == g[f"{tag}_res"]).all() and (states_s == g[f"{tag}_states"]).all()
+	np.random.seed(9)
 	res_b, states_b, times_b = ev.eval_batched(AStarBatch(net, lambda_=0.2, expansions=20))
 	assert (res_b == g[f"{tag}_res"]).all() and (states_b == g[f"{tag}_states"]).all()
 	assert Evaluator.states_per_sec(states_b, times_b).shape == (res.size,)
@@ -110,7 +115,7 @@ def test_evaluator_matches_reference(golden, tag):
 def test_train_with_evaluator_hook_runs_and_tracks_best_net():
 	"""Evaluation rollouts (train.py:211-227): the agent's net is swapped in, solve rates are recorded, best net is a copy."""
 	from rl_rubiks_b200.evaluation import Evaluator
-	from rl_rubiks_b200.frontier import AStar
+	from tests.agent_harness import AStar
 	from rl_rubiks_b200.train import Train
 	torch.manual_seed(0)
 	net = _SmallNet().cuda()
@@ -150,3 +155,28 @@ def test_bf16_rows_keep_search_traces_and_train():
 	assert np.isfinite(losses[torch.bfloat16]).all()
 	print("bf16 vs f32 training losses, max relative deviation:", np.abs(losses[torch.bfloat16] / losses[torch.float32] - 1).max())
 	np.testing.assert_allclose(losses[torch.bfloat16], losses[torch.float32], rtol=0.05)      # bf16 GEMMs: ~3 significant digits
+
+
+def test_evaluator_batched_draw_equals_sequential_draws():
+	"""`Evaluator._draw` scrambles in batches but must consume the numpy stream like the reference's loop, including the redraws
+	of `cube.scramble(depth, force_not_solved=True)` (depth-2 scrambles come out solved one time in twelve)."""
+	from rl_rubiks_b200 import cube
+	from rl_rubiks_b200.evaluation import Evaluator
+	for depths, n_games, seed in (([2, 1, 2, 4, 0, 2], 40, 0), (range(0), 5, 3), ([2], 150, 7)):
+		ev = Evaluator(n_games, depths, max_states=10)
+		np.random.seed(seed)
+		got = ev._draw()
+		end_state = np.random.get_state()[1].copy()
+		np.random.seed(seed)
+		want = []
+		for d in ev.scrambling_depths:
+			for _ in range(n_games):
+				if ev._isdeep():
+					d = np.random.randint(100, 1000)
+				state, _, _ = cube.scramble(int(d), True)
+				want.append((state, int(d)))
+		assert (np.random.get_state()[1] == end_state).all()
+		assert len(got) == len(want)
+		for (s1, d1), (s2, d2) in zip(got, want):
+			assert d1 == d2 and (s1 == s2).all()
+			assert d1 == 0 or not cube.is_solved(s1)
