@@ -125,6 +125,13 @@ int rb_seeded_actions(uint64_t seed, uint64_t first_cube, uint8_t* actions, int6
  * Halves the host->device bytes of a host-drawn scramble (rbh_scramble_packed). */
 int rb_unpack_actions(const uint8_t* packed, uint8_t* actions, int64_t n, int32_t depth, rb_stream_t stream);
 
+/* The same cube in the other representation (the two are isomorphic: cube.py:149-173 maps both to the 6x3x3 sticker view).
+ * rb_as686: int8 [n][20] -> int8 [n][6][8][6].  rb_as2024: int8 [n][6][8][6] -> int8 [n][20]; ok (uint8 [n], may be NULL) is
+ * cleared for rows that are not a reachable cube (their values are 255).  The batched A* keeps its stored states in the
+ * 20-byte form whatever the caller's representation and renders 6x8x6 rows only for the value net's input. */
+int rb_as686(const int8_t* states2024, int8_t* states686, int64_t n, rb_stream_t stream);
+int rb_as2024(const int8_t* states686, int8_t* states2024, uint8_t* ok, int64_t n, rb_stream_t stream);
+
 /* ---- ADI training batch (librubiks/train.py:256-339) --------------------------------------- */
 /* Fused generator, train.py:277-296 in one launch: sequence scramble -> 12 children of every state ->
  * one-hot of states and of children -> solved flags of both.  n = games*depth.

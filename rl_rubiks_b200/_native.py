@@ -64,6 +64,8 @@ SIGNATURES = {
 	"rb_astar_init": (C.c_int, [_p, _p, _p]),
 	"rb_astar_expand": (C.c_int, [_p, _i64, _p, _p, _p, _p, _p, _p]),
 	"rb_astar_commit": (C.c_int, [_p, _p, _f64, _p, _p, _p, _p]),
+	"rb_as686": (C.c_int, [_p, _p, _i64, _p]),
+	"rb_as2024": (C.c_int, [_p, _p, _p, _i64, _p]),
 	"rb_scramble_seeded": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, _p, _p, _i64, _i32, _p]),
 	"rb_seeded_actions": (C.c_int, [C.c_uint64, C.c_uint64, _p, _i64, _i32, _p]),
 	"rb_unpack_actions": (C.c_int, [_p, _p, _i64, _i32, _p]),

@@ -299,7 +299,8 @@ k_scramble(const uint8_t* __restrict__ actions, int64_t stride_cube, int64_t str
 // In place: the 20x24 state is parked in the first 20 bytes of each 288-byte output row.  Warp per cube.
 constexpr int kStickerDst = 20 * 24 * 3, kStickerBytes = kStickerDst + 20 * 3 + 4;
 __global__ void __launch_bounds__(kThreads)
-k_render_from2024(int8_t* __restrict__ io, const int8_t* __restrict__ start, int64_t n) {
+k_render_from2024(int8_t* __restrict__ io, const int8_t* __restrict__ start, int64_t n, const int8_t* __restrict__ parked = nullptr) {
+	// parked != nullptr: the 20x24 states come from their own int8 [n][20] array instead of the heads of the output rows
 	__shared__ __align__(16) uint8_t s_tab[kStickerBytes];
 	__shared__ __align__(16) uint8_t s_out[kWarps][kStateBytes];
 	__shared__ __align__(16) uint8_t s_src[kWarps][kStateBytes];
@@ -334,9 +335,15 @@ k_render_from2024(int8_t* __restrict__ io, const int8_t* __restrict__ start, int
 	auto fetch_parked = [&](int64_t c) {
 		const int64_t cube = c * 32 + lane;
 		if (c < n_chunks && cube < n) {
-			const uint4 q = *reinterpret_cast<const uint4*>(io + cube * kStateBytes);
-			pk[0] = q.x; pk[1] = q.y; pk[2] = q.z; pk[3] = q.w;
-			pk[4] = *reinterpret_cast<const uint32_t*>(io + cube * kStateBytes + 16);
+			if (parked) {
+				const uint32_t* q = reinterpret_cast<const uint32_t*>(parked + cube * 20);
+#pragma unroll
+				for (int k = 0; k < 5; ++k) pk[k] = q[k];
+			} else {
+				const uint4 q = *reinterpret_cast<const uint4*>(io + cube * kStateBytes);
+				pk[0] = q.x; pk[1] = q.y; pk[2] = q.z; pk[3] = q.w;
+				pk[4] = *reinterpret_cast<const uint32_t*>(io + cube * kStateBytes + 16);
+			}
 		}
 	};
 	uint4 src_next = make_uint4(0u, 0u, 0u, 0u);
@@ -377,6 +384,34 @@ k_render_from2024(int8_t* __restrict__ io, const int8_t* __restrict__ start, int
 			if (lane < 18) rb_st_stream(reinterpret_cast<uint4*>(row) + lane, reinterpret_cast<const uint4*>(s_out[wib])[lane], RB_STORE_CS);
 			__syncwarp();
 		}
+	}
+}
+
+// 6x8x6 state -> the 20x24 state of the same cube: cubie c has value v iff every sticker k of c shows its home colour in slot
+// dst[c][v][k] (the sticker tables of rb_tables.cuh read the other way round).  Thread per (state, cubie); value 255 and
+// ok = 0 when no value fits (not a reachable cube).  Used to run searches on the 20-byte representation whatever the caller's.
+__global__ void __launch_bounds__(kThreads)
+k_as2024(const int8_t* __restrict__ states, int8_t* __restrict__ out, uint8_t* __restrict__ ok, int64_t n) {
+	__shared__ __align__(16) uint8_t s_tab[kStickerBytes];
+	for (int i = threadIdx.x; i < kStickerBytes / 4; i += blockDim.x)
+		reinterpret_cast<uint32_t*>(s_tab)[i] = reinterpret_cast<const uint32_t*>(g_stickers686)[i];
+	__syncthreads();
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n * 20; t += stride) {
+		const int64_t i = t / 20;
+		const int c = (int)(t - i * 20), K = c < 8 ? 3 : 2;
+		const int8_t* st = states + i * kStateBytes;
+		int found = 255;
+		for (int v = 0; v < 24; ++v) {
+			bool fits = true;
+			for (int k = 0; k < K; ++k) {
+				const int slot = s_tab[(c * 24 + v) * 3 + k], colour = s_tab[kStickerDst + c * 3 + k] >> 3;
+				fits = fits && st[slot * 6 + colour] == 1;
+			}
+			if (fits && found == 255) found = v;
+		}
+		out[i * 20 + c] = (int8_t)found;
+		if (found == 255 && ok) ok[i] = 0;
 	}
 }
 

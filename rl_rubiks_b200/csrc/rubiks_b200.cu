@@ -574,7 +574,17 @@ int rb_astar_expand(const rb_astar_view* a, int64_t max_states, int8_t* new_stat
 	cudaStream_t st = S(stream);
 	const dim3 grid(v.nbx(), v.K);
 	RB_CUDA(cudaMemsetAsync(n_active, 0, sizeof(int32_t), st));
-	RB_CUDA(cudaFuncSetAttribute(rba::k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, rba::kSelSmem));   // per device, cheap
+	{
+		static std::mutex mu;                                    // once per device, and never inside a stream capture of the step
+		static bool done[64] = {};
+		int dev = 0;
+		RB_CUDA(cudaGetDevice(&dev));
+		std::lock_guard<std::mutex> lock(mu);
+		if (dev >= 0 && dev < 64 && !done[dev]) {
+			RB_CUDA(cudaFuncSetAttribute(rba::k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, rba::kSelSmem));
+			done[dev] = true;
+		}
+	}
 	rba::k_select<<<v.K, rba::kSelThreads, rba::kSelSmem, st>>>(v, max_states, n_active);
 	RB_LAUNCHED("astar_select");
 	rba::k_probe<<<grid, rba::kThreads, 0, st>>>(v);
@@ -631,6 +641,29 @@ int rb_scramble_seeded(int rep, uint64_t seed, uint64_t first_cube, const int8_t
 	int rc = rbs::launch_seeded(seed, first_cube, out, n, depth, S(stream), rb686::kStateBytes);    // 20x24 state parked at the row head
 	if (rc != RB_OK) return rc;
 	rb686::k_render_from2024<<<rb_grid((n + 31) / 32, rb686::kWarps, 8), rb686::kThreads, 0, S(stream)>>>(out, start, n);
+	RB_LAUNCHED("render_686");
+	return RB_OK;
+}
+
+int rb_as2024(const int8_t* states686, int8_t* states2024, uint8_t* ok, int64_t n, rb_stream_t stream) {
+	RB_REQUIRE(n >= 0, "bad size");
+	if (n == 0) return RB_OK;
+	RB_REQUIRE(states686 && states2024, "null pointer");
+	RB_REQUIRE(rbt::host().stickers_ok, "sticker tables: the 20x24 and 6x8x6 move tables disagree");
+	RB_INIT();
+	if (ok) RB_CUDA(cudaMemsetAsync(ok, 1, (size_t)n, S(stream)));
+	rb686::k_as2024<<<rb_grid(n * 20, rb686::kThreads, 8), rb686::kThreads, 0, S(stream)>>>(states686, states2024, ok, n);
+	RB_LAUNCHED("as2024");
+	return RB_OK;
+}
+
+int rb_as686(const int8_t* states2024, int8_t* states686, int64_t n, rb_stream_t stream) {
+	RB_REQUIRE(n >= 0, "bad size");
+	if (n == 0) return RB_OK;
+	RB_REQUIRE(states2024 && states686 && aligned(states2024, 4) && aligned(states686, 16), "null or misaligned pointer");
+	RB_REQUIRE(rbt::host().stickers_ok, "sticker tables: the 20x24 and 6x8x6 move tables disagree");
+	RB_INIT();
+	rb686::k_render_from2024<<<rb_grid((n + 31) / 32, rb686::kWarps, 8), rb686::kThreads, 0, S(stream)>>>(states686, nullptr, n, states2024);
 	RB_LAUNCHED("render_686");
 	return RB_OK;
 }

@@ -240,6 +240,28 @@ def as_correct(t: torch.Tensor) -> torch.Tensor:
 	return out
 
 
+def to_686(states2024):
+	"""The same cubes in the 6x8x6 representation: (n, 20) -> (n, 6, 8, 6).  (The reference converts both to the 6x3x3 sticker
+	view, cube.py:149-173; the library goes from one to the other directly, on the device.)"""
+	was_np = not isinstance(states2024, torch.Tensor)
+	s = (torch.from_numpy(np.ascontiguousarray(states2024, dtype=np.int8)) if was_np else states2024).to(device=_dev(), dtype=torch.int8).reshape(-1, 20).contiguous()
+	out = torch.empty(s.shape[0], 6, 8, 6, dtype=torch.int8, device=s.device)
+	N.check(N.lib.rb_as686(N.ptr(s), N.ptr(out), s.shape[0], N.stream_handle()))
+	return _out(out, was_np)
+
+
+def to_2024(states686):
+	"""(n, 6, 8, 6) -> (n, 20); IndexError if a state is not a reachable cube."""
+	was_np = not isinstance(states686, torch.Tensor)
+	s = (torch.from_numpy(np.ascontiguousarray(states686, dtype=np.int8)) if was_np else states686).to(device=_dev(), dtype=torch.int8).reshape(-1, 6, 8, 6).contiguous()
+	out = torch.empty(s.shape[0], 20, dtype=torch.int8, device=s.device)
+	ok = torch.empty(s.shape[0], dtype=torch.uint8, device=s.device)
+	N.check(N.lib.rb_as2024(N.ptr(s), N.ptr(out), N.ptr(ok), s.shape[0], N.stream_handle()))
+	if not bool(ok.all().item()):
+		raise IndexError("a 6x8x6 state is not a reachable cube")
+	return _out(out, was_np)
+
+
 # ---- action logic (cube.py:142-147, 179-200) -------------------------------------------------------
 def repeat_state(state: np.ndarray, n: int = action_dim) -> np.ndarray:
 	"""n copies of one state, shape (n, *shape()) (cube.py:142-147)."""

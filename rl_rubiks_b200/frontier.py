@@ -254,17 +254,26 @@ class AStarBatch:
 	list, seen-set, G / parent relaxation and the pop of the N cheapest states per search are kernels (csrc/rb_astar.cuh);
 	the host only runs the value net on the contiguous batch of new states of all searches and reads two counters per step.
 	Every search follows the reference's trace exactly (same pops, same state numbering, same G / parents / action queue).
-	20x24 representation."""
 
-	def __init__(self, net, lambda_: float, expansions: int, oh_dtype=torch.float32):
+	Both representations (the module flag, or `is2024`): the searches always run on the 20-byte states -- the two
+	representations describe the same cube, children come in the same action order, so the trace is the same -- and with the
+	6x8x6 representation the roots are converted on the way in (`rb_as2024`) and the new states are rendered as 6x8x6 rows
+	(`rb_as686`) only to feed the value net its 288-wide one-hot.
+
+	The launches of a step are two CUDA graphs (expand: 6 kernels + 1 memset, commit: 6 kernels), captured once per buffer set."""
+
+	def __init__(self, net, lambda_: float, expansions: int, oh_dtype=torch.float32, is2024: bool | None = None, use_graphs: bool = True):
 		N.require_cuda()
 		if not 0 < expansions <= 1024:
 			raise ValueError("expansions must be in 1..1024")
 		self.net, self.lambda_, self.expansions = net, float(lambda_), int(expansions)
+		self.is2024 = cube.get_is2024() if is2024 is None else bool(is2024)
 		# torch.bfloat16 (opt-in, not the reference's dtype): bf16 one-hot rows and a bf16-autocast forward of the value net
 		self.oh_dtype = oh_dtype
 		self._as_oh = cube._oh_fn("rb_as_oh", oh_dtype)
 		self.dev = torch.device("cuda", torch.cuda.current_device())
+		self.use_graphs = use_graphs
+		self.action_queue = deque()
 
 	def _alloc(self, K: int, max_states: int):
 		dev, Nx = self.dev, self.expansions
@@ -286,7 +295,7 @@ class AStarBatch:
 		self.sel = torch.zeros(K, Nx, dtype=torch.int32, device=dev)
 		self.won = torch.zeros(K, dtype=torch.uint8, device=dev)
 		self.solved_index = torch.zeros(K, dtype=torch.int32, device=dev)
-		self.capacity = _pow2_at_least(2 * K * M)
+		self.capacity = _pow2_at_least(2 * K * M)                 # load <= 1/2 by construction: a search stores at most M states
 		self.table = torch.empty(N.lib.rb_hashset_bytes(self.capacity), dtype=torch.uint8, device=dev)
 		self.scratch = torch.empty(N.lib.rb_astar_scratch_bytes(K, Nx), dtype=torch.uint8, device=dev)
 		P = 12 * Nx
@@ -294,10 +303,14 @@ class AStarBatch:
 		self.new_search = torch.empty(K * P, dtype=torch.int32, device=dev)
 		self.new_index = torch.empty(K * P, dtype=torch.int32, device=dev)
 		self.counters = torch.zeros(2, dtype=torch.int32, device=dev)          # n_new_total, n_active
-		self.oh = torch.empty(K * P, 480, dtype=self.oh_dtype, device=dev)
+		self.counters_host = torch.zeros(2, dtype=torch.int32, pin_memory=True)
+		self.values = torch.zeros(K * P, dtype=torch.float32, device=dev)      # the net's output lands here: fixed address for the commit graph
+		self.oh = torch.empty(K * P, 480 if self.is2024 else 288, dtype=self.oh_dtype, device=dev)
+		self.new_states686 = None if self.is2024 else torch.empty(K * P, 6, 8, 6, dtype=torch.int8, device=dev)
 		self.view = N.AStarView(K, M, Nx, *(N.ptr(t) for t in (self.states, self.G, self.parents, self.parent_actions, self.cost, self.in_open,
 																 self.count, self.n_sel, self.sel, self.won, self.solved_index, self.table)),
 								self.capacity, N.ptr(self.scratch))
+		self._graphs = None
 
 	# ---- the reference agents' interface, one cube (agents.py:221-252) ----
 	_default_max_states = 1 << 20              # buffers are sized by the state budget: a search limited by time only gets this one
@@ -319,42 +332,97 @@ class AStarBatch:
 	def __str__(self):
 		return f"AStar (lambda={self.lambda_}, N={self.expansions})"
 
+	def _roots(self, states) -> torch.Tensor:
+		s = states if isinstance(states, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(states, dtype=np.int8))
+		s = s.to(device=self.dev, dtype=torch.int8)
+		if self.is2024:
+			return s.reshape(-1, 20).contiguous()
+		s = s.reshape(-1, 6, 8, 6).contiguous()
+		roots = torch.empty(s.shape[0], 20, dtype=torch.int8, device=self.dev)
+		ok = torch.empty(s.shape[0], dtype=torch.uint8, device=self.dev)
+		N.check(N.lib.rb_as2024(N.ptr(s), N.ptr(roots), N.ptr(ok), s.shape[0], N.stream_handle()))
+		if not bool(ok.all().item()):
+			raise IndexError("a 6x8x6 start state is not a reachable cube")
+		return roots
+
+	def _step_calls(self, max_states: int):
+		"""The two halves of a step as callables: plain C-ABI calls, or replays of their CUDA graphs (captured once per buffer set
+		and budget; the graphs hold kernel launches only -- the value net runs between them, on however many new states there are)."""
+		import ctypes as C
+		v = C.byref(self.view)
+		n_total_ptr, n_active_ptr = C.c_void_p(self.counters.data_ptr()), C.c_void_p(self.counters.data_ptr() + 4)
+
+		def expand():
+			N.check(N.lib.rb_astar_expand(v, int(max_states), N.ptr(self.new_states), N.ptr(self.new_search), N.ptr(self.new_index),
+										  n_total_ptr, n_active_ptr, N.stream_handle()))
+
+		def commit():
+			N.check(N.lib.rb_astar_commit(v, N.ptr(self.values), self.lambda_, N.ptr(self.new_search), N.ptr(self.new_index), n_total_ptr,
+										  N.stream_handle()))
+
+		if not self.use_graphs:
+			return expand, commit
+		if self._graphs is None or self._graphs[0] != int(max_states):
+			ge, gc = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+			with torch.cuda.graph(ge):
+				expand()
+			with torch.cuda.graph(gc):
+				commit()
+			self._graphs = (int(max_states), ge, gc)
+		return self._graphs[1].replay, self._graphs[2].replay
+
 	@torch.no_grad()
 	def search_many(self, states, max_states: int, max_steps: int | None = None, time_limit: float | None = None):
-		"""states: (K, 20) int8 (numpy or CUDA tensor).  Returns (solved bool (K,), action queues: list of K lists,
+		"""states: (K, *shape) int8 (numpy or CUDA tensor).  Returns (solved bool (K,), action queues: list of K lists,
 		len per search int (K,)), the three things `AStar.search` leaves behind for one cube."""
-		import ctypes as C
 		t0 = perf_counter()
-		s = states if isinstance(states, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(states, dtype=np.int8))
-		roots = s.to(device=self.dev, dtype=torch.int8).reshape(-1, 20).contiguous()
+		roots = self._roots(states)
 		self._alloc(roots.shape[0], int(max_states))
 		self.net.eval()
 		sh = N.stream_handle()
-		v = C.byref(self.view)
-		N.check(N.lib.rb_hashset_clear(N.ptr(self.table), self.capacity, sh))
-		N.check(N.lib.rb_astar_init(v, N.ptr(roots), sh))
-		n_total_ptr, n_active_ptr = C.c_void_p(self.counters.data_ptr()), C.c_void_p(self.counters.data_ptr() + 4)
-		self.steps = 0
+		import ctypes as C
+		def start():
+			N.check(N.lib.rb_hashset_clear(N.ptr(self.table), self.capacity, sh))
+			N.check(N.lib.rb_astar_init(C.byref(self.view), N.ptr(roots), sh))
+
+		if self.use_graphs and self._graphs is None:
+			# one plain expansion before the capture (tables uploaded, function attributes set: nothing of that may happen inside
+			# a capture), then everything is initialised again
+			start()
+			N.check(N.lib.rb_astar_expand(C.byref(self.view), int(max_states), N.ptr(self.new_states), N.ptr(self.new_search), N.ptr(self.new_index),
+										  C.c_void_p(self.counters.data_ptr()), C.c_void_p(self.counters.data_ptr() + 4), sh))
+			torch.cuda.current_stream().synchronize()
+		start()
+		expand, commit = self._step_calls(max_states)
+		self.steps = self.launches = 0
+		l0 = N.lib.rb_launch_count()
 		while (max_steps is None or self.steps < max_steps) and (time_limit is None or perf_counter() - t0 < time_limit):
-			N.check(N.lib.rb_astar_expand(v, int(max_states), N.ptr(self.new_states), N.ptr(self.new_search), N.ptr(self.new_index),
-										  n_total_ptr, n_active_ptr, sh))
-			n_total, n_active = (int(x) for x in self.counters.tolist())         # the one host sync of a step
+			expand()
+			self.counters_host.copy_(self.counters, non_blocking=True)           # the one host sync of a step
+			torch.cuda.current_stream().synchronize()
+			n_total, n_active = (int(x) for x in self.counters_host.tolist())
 			if n_active == 0:
 				break
-			values = self._values(n_total)
-			N.check(N.lib.rb_astar_commit(v, N.ptr(values), self.lambda_, N.ptr(self.new_search), N.ptr(self.new_index), n_total_ptr, sh))
+			self._values(n_total)
+			commit()
 			self.steps += 1
+		self.launches = N.lib.rb_launch_count() - l0
 		return self._results()
 
-	def _values(self, n: int) -> torch.Tensor:
-		"""agents.py:379-381: one-hot born on the device, value head only; f32 (n,)."""
+	def _values(self, n: int):
+		"""agents.py:379-381: one-hot born on the device, value head only; the f32 values land in `self.values[:n]`."""
 		if n == 0:
-			return torch.zeros(1, dtype=torch.float32, device=self.dev)
+			return
 		oh = self.oh[:n]
-		N.check(self._as_oh(N.REP_2024, N.ptr(self.new_states), N.ptr(oh), n, N.stream_handle()))
+		src = self.new_states
+		rep = N.REP_2024
+		if not self.is2024:
+			N.check(N.lib.rb_as686(N.ptr(self.new_states), N.ptr(self.new_states686), n, N.stream_handle()))
+			src, rep = self.new_states686, N.REP_686
+		N.check(self._as_oh(rep, N.ptr(src), N.ptr(oh), n, N.stream_handle()))
 		with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.oh_dtype == torch.bfloat16):
 			val = self.net(oh, value=True, policy=False)
-		return val.reshape(-1).float().contiguous()
+		self.values[:n].copy_(val.reshape(-1))
 
 	def _results(self):
 		won = self.won.bool().cpu().numpy()

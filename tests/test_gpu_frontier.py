@@ -331,3 +331,58 @@ def test_astar_batch_matches_single_search_traces(golden, n_exp, max_states, lam
 	# a second call on the same agent reuses every buffer and must reproduce the run
 	won2, queues2, count2 = agent.search_many(starts, max_states)
 	assert (won2 == won).all() and (count2 == count).all() and queues2 == queues
+
+
+def test_representation_conversion_round_trip():
+	"""rb_as686 / rb_as2024: the same move sequence applied in either representation gives states that convert into each other."""
+	from rl_rubiks_b200 import cube
+	g = np.random.RandomState(0)
+	f, d = g.randint(0, 6, (3000, 25)), g.randint(0, 2, (3000, 25))
+	s2024, s686 = O.scramble_many(f, d, True), O.scramble_many(f, d, False)
+	s2024[0], s686[0] = O.solved(True), O.solved(False)
+	assert (cube.to_686(s2024) == s686).all()
+	assert (cube.to_2024(s686) == s2024).all()
+	bad = s686[:3].copy()
+	bad[1, 0, 0] = bad[1, 1, 0]                               # two stickers of one corner show colours no corner has
+	with pytest.raises(IndexError):
+		cube.to_2024(bad)
+
+
+@pytest.mark.parametrize("use_graphs", [True, False])
+def test_astar_batch_686_matches_harness_traces(golden, use_graphs):
+	"""AStarBatch under the 6x8x6 representation (searches run on the 20-byte states, 288-wide one-hot rows for the net) against
+	the single-search harness on the 6x8x6 states themselves and against the reference's recorded 6x8x6 trace."""
+	from rl_rubiks_b200 import cube
+	from rl_rubiks_b200.frontier import AStarBatch
+	from tests.agent_harness import AStar
+	g = golden("search")
+	w = g["astar_w_686"]
+	rng = np.random.RandomState(4)
+	starts = [g["astar_start_686"], O.solved_686()]
+	for depth in (1, 2, 3, 4, 5, 7):
+		starts.append(O.scramble(rng.randint(0, 6, depth), rng.randint(0, 2, depth), False))
+	starts = np.stack(starts)
+	cube.set_is2024(False)
+	batch = AStarBatch(_FakeNet(w), lambda_=0.16, expansions=7, use_graphs=use_graphs)
+	assert not batch.is2024
+	won, queues, count = batch.search_many(starts, 2000)
+	for s, start in enumerate(starts):
+		single = AStar(_FakeNet(w), lambda_=0.16, expansions=7)
+		ok = single.search(start, None, 2000)
+		assert bool(won[s]) == ok and (count[s] == len(single) or (ok and len(single) == 0)), (s, won[s], ok, count[s], len(single))
+		assert queues[s] == list(single.action_queue)
+		L = len(single)
+		if L:
+			assert (cube.to_686(batch.states[s, 1:L + 1]).cpu().numpy() == single.states[1:L + 1].cpu().numpy()).all()
+			assert (batch.G[s, 1:L + 1].cpu().numpy() == single.G[1:L + 1]).all()
+			assert (batch.parents[s, 2:L + 1].cpu().numpy() == single.parents[2:L + 1]).all()
+	# the reference's own recorded trace of search 0 (12 expansion steps)
+	L = int(g["astar_lens_686"][-1])
+	if not bool(g["astar_won_686"]) and count[0] >= L:
+		assert (cube.to_686(batch.states[0, 1:L + 1]).cpu().numpy() == g["astar_states_686"]).all()
+	cube.set_is2024(True)
+	# the one-cube agent interface against the reference's recorded full search (agents.py:221-252)
+	one = AStarBatch(_FakeNet(np.zeros(480)), lambda_=1.0, expansions=5, use_graphs=use_graphs)
+	assert one.search(g["astar_full_start"], None, 20000) == bool(g["astar_full_ok"])
+	assert len(one) == int(g["astar_full_len"]) and list(one.action_queue) == g["astar_full_queue"].tolist()
+	assert one.search(O.solved_2024(), None, 100) and len(one) == 0 and not one.action_queue

@@ -2,7 +2,8 @@
 """BASELINE configs[3]: batched weighted A* on K cubes scrambled `depth` moves deep, lambda = 0.16, N = 700
 (configs/main_eval.ini:8-9), max_states = 175000 (runeval.py:43), random-init value MLP of the reference's fc_small shape
 (model.py:143-161: 480 -> 4096 -> 2048 -> 512 -> 1, ELU + BatchNorm1d) as a plain torch module.
-Reports states/s with the net included and, with --cheap-net, the frontier machinery alone."""
+Reports states/s with the net included and the frontier machinery alone (--cheap-net: a 480 -> 32 -> 1 net; --null-net: the
+values are zeros and no GEMM runs at all), the library's kernel launches per step and the CUDA-graph launches per step."""
 import argparse
 import os
 import sys
@@ -41,6 +42,8 @@ def main():
 	ap.add_argument("--max-states", type=int, default=175000)
 	ap.add_argument("--lam", type=float, default=0.16)
 	ap.add_argument("--cheap-net", action="store_true")
+	ap.add_argument("--null-net", action="store_true", help="value net replaced by zeros: one-hot rows + frontier kernels only")
+	ap.add_argument("--no-graphs", action="store_true", help="plain launches instead of the two CUDA graphs per step")
 	ap.add_argument("--tf32", action="store_true")
 	ap.add_argument("--bf16", action="store_true", help="bf16 one-hot rows + bf16 autocast value forward (opt-in)")
 	args = ap.parse_args()
@@ -48,17 +51,25 @@ def main():
 	torch.backends.cuda.matmul.allow_tf32 = args.tf32
 	dev = torch.device("cuda", 0)
 	net = ValueMLP(args.cheap_net).to(dev).eval()
+	if args.null_net:
+		class Null(torch.nn.Module):
+			def forward(self, x, policy=False, value=True):
+				return x.new_zeros(x.shape[0], 1, dtype=torch.float32)
+		net = Null()
 	g = torch.Generator(device=dev); g.manual_seed(0)
 	acts = torch.randint(0, 12, (args.cubes, args.depth), dtype=torch.uint8, device=dev, generator=g)
 	starts = cube.scramble_batch(acts)
-	agent = frontier.AStarBatch(net, args.lam, args.expansions, oh_dtype=torch.bfloat16 if args.bf16 else torch.float32)
+	agent = frontier.AStarBatch(net, args.lam, args.expansions, oh_dtype=torch.bfloat16 if args.bf16 else torch.float32,
+								use_graphs=not args.no_graphs)
 	agent.search_many(starts, args.max_states, max_steps=1)           # warm-up: buffer allocation (~25 GB at 1000 cubes), cuBLAS heuristics
 	torch.cuda.synchronize()
 	t0 = time.perf_counter()
 	won, queues, count = agent.search_many(starts, args.max_states)
 	torch.cuda.synchronize()
 	dt = time.perf_counter() - t0
-	print(f"cubes {args.cubes} depth {args.depth} N {args.expansions} max_states {args.max_states} net {'cheap' if args.cheap_net else 'fc_small'}"
+	per_step = agent.launches / max(agent.steps, 1)
+	print(f"[kernels of the library per step {per_step:.1f}; host launches per step: {'2 graphs + one-hot' if not args.no_graphs else f'{per_step:.0f} kernels'} + the net] "
+		  f"cubes {args.cubes} depth {args.depth} N {args.expansions} max_states {args.max_states} net {'null' if args.null_net else 'cheap' if args.cheap_net else 'fc_small'}"
 		  f"{' tf32' if args.tf32 else ''}{' bf16' if args.bf16 else ''}: steps {agent.steps} solved {int(won.sum())} states {int(count.sum())} in {dt:.3f} s = "
 		  f"{count.sum() / dt / 1e6:.2f} M states/s ({count.sum() / max(agent.steps, 1) / args.cubes:.0f} new states/step/cube)")
 
