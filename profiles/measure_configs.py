@@ -99,7 +99,16 @@ def main():
 		out = torch.empty(n, 20, dtype=torch.int8, device=dev)
 		report("scramble_2024 (C2: n x 100 moves, final state)", n * 120, n * depth, "moves",
 			   lambda: N.check(N.lib.rb_scramble(N.REP_2024, N.ptr(acts), depth, 1, None, N.ptr(out), n, depth, sh)), n=n)
-		del acts, out
+		acts_t = acts.t().contiguous()
+		report("scramble_2024 move-major actions [100][n] (the reference's draw shape)", n * 120, n * depth, "moves",
+			   lambda: N.check(N.lib.rb_scramble(N.REP_2024, N.ptr(acts_t), 1, n, None, N.ptr(out), n, depth, sh)), n=n)
+		del acts_t
+		report("scramble_seeded_2024 (moves drawn in the kernel: 20 B per cube)", n * 20, n * depth, "moves",
+			   lambda: N.check(N.lib.rb_scramble_seeded(N.REP_2024, 7, 0, None, N.ptr(out), n, depth, sh)), n=n)
+		packed = (acts[:, 0::2] + 13 * acts[:, 1::2]).contiguous()
+		report("unpack_actions (two moves per byte -> action bytes)", n * 150, n * depth, "moves",
+			   lambda: N.check(N.lib.rb_unpack_actions(N.ptr(packed), N.ptr(acts), n, depth, sh)), n=n)
+		del acts, out, packed
 	if want("multi_rotate_2024"):
 		n = (1 << 24) // q
 		s = scrambled_2024(n)

@@ -169,6 +169,110 @@ def test_macro3_inverse_sequence_emulation_matches_oracle(depth):
 	assert (_emulate_inverse(actions, rows, rows3) == O.scramble_many(f, d, True)).all()
 
 
+# ---- the kernels' other row / fold schedules -------------------------------------------------------------------------------
+# A schedule is a list of ("r3", p): the 3-move row of moves p-3, p-2, p-1; ("r2", p, k): the 2-move row of the k (1 or 2) moves
+# ending at p; ("fold",).  The twist accumulators have 5 bits: a schedule with more than 10 rows between two folds could carry
+# into the id bits -- `apply` below asserts that it never happens.
+def _run_schedule(actions, rows, rows3, schedule):
+	n, depth = actions.shape
+	inv = actions.astype(np.int64) ^ 1
+	C = np.tile((np.arange(8, dtype=np.uint8) << 5).astype(np.uint8), (n, 1))
+	E = np.tile(np.arange(12, dtype=np.uint8), (n, 1))
+	covered = []
+	for op in schedule:
+		if op[0] == "fold":
+			C = _fold(C)
+			continue
+		if op[0] == "r3":
+			p = op[1]
+			r = rows3[inv[:, p - 1] + 12 * inv[:, p - 2] + 144 * inv[:, p - 3]]
+			covered += [p - 1, p - 2, p - 3]
+		else:
+			_, p, k = op
+			r = rows[inv[:, p - 1] + 13 * (inv[:, p - 2] if k == 2 else np.full(n, 12, np.int64))]
+			covered += [p - 1] + ([p - 2] if k == 2 else [])
+		sc, tf = r[:, 0], r[:, 4]
+		c0 = _prmt(C[:, :4], C[:, 4:], sc).astype(np.int64) + _bytes_of(tf & 0x03030303)
+		c1 = _prmt(C[:, :4], C[:, 4:], sc >> 16).astype(np.int64) + _bytes_of((tf >> 2) & 0x03030303)
+		assert ((c0 & 31) >= _bytes_of(tf & 0x03030303)).all() and ((c1 & 31) >= _bytes_of((tf >> 2) & 0x03030303)).all()    # no carry out of the 5 bits
+		C = np.concatenate([c0, c1], 1).astype(np.uint8)
+		Es = []
+		for d in range(3):
+			sel = r[:, 1 + d]
+			x = _prmt(E[:, :4], E[:, 4:8], sel)
+			Es.append(_prmt(x, E[:, 8:], sel >> 16) ^ _bytes_of(tf & (0x10101010 << d)))
+		E = np.concatenate(Es, 1)
+	assert covered == list(range(depth - 1, -1, -1))            # every move exactly once, last move first
+	out = np.zeros((n, 20), dtype=np.int8)
+	pc, t = (C >> 5).astype(np.int64), (C & 31).astype(np.int64) % 3
+	out[:, :8] = 3 * pc + np.where(np.isin(pc, (0, 2, 5, 7)), t, (3 - t) % 3)
+	out[:, 8:] = 2 * (E & 15).astype(np.int64) + (((E >> 4) ^ (E >> 5) ^ (E >> 6)) & 1)
+	return out
+
+
+def _schedule_a16(depth):
+	"""k_scramble_macro3 mode 2 / 3 (depth % 16 == 0): pairs of 24-move groups anchored at multiples of 48 from the row start; what
+	lies above them -- an odd group and / or a remainder of 8 or 16 moves -- goes first (rb_scramble_macro.cuh, `if (a16)`)."""
+	assert depth % 16 == 0
+	M = depth - depth % 24
+	rem, top, odd = depth - M, (M // 48) * 48, (M // 24) & 1
+	words12 = lambda p: [("r3", p), ("r3", p - 3), ("r3", p - 6), ("r3", p - 9)]                     # apply_words: 12 moves ending at p
+	rem8 = lambda p: [("r3", p), ("r3", p - 3), ("r2", p - 6, 2)]
+	rem4 = lambda p: [("r3", p), ("r2", p - 3, 1)]
+	sch = []
+	base = top + (24 if odd else 0)                                                                   # the remainder starts here
+	if rem == 8:
+		sch += rem8(base + 8) + [("fold",)]
+	elif rem == 16:
+		sch += words12(base + 16) + rem4(base + 4) + [("fold",)]
+	if odd:
+		sch += words12(top + 24) + words12(top + 12) + [("fold",)]
+	for m in range(top, 0, -48):
+		sch += words12(m) + words12(m - 12) + [("fold",)] + words12(m - 24) + words12(m - 36) + [("fold",)]
+	return sch
+
+
+def _schedule_seeded(depth):
+	"""k_scramble_seeded: the trailing depth % 3 moves first, then the triples from the last to the first, four per Philox block;
+	folds after the top block plus one, then after every second block, and at the end."""
+	Q, rem = depth // 3, depth % 3
+	n_words = Q + (1 if rem else 0)
+	n_blocks = (n_words + 3) // 4
+	sch, since = [], 0
+	for j in range(n_blocks - 1, -1, -1):
+		for k in (3, 2, 1, 0):
+			q = 4 * j + k
+			if q > Q or (q == Q and rem == 0):
+				continue
+			sch.append(("r2", depth, rem) if q == Q else ("r3", 3 * q + 3))
+		since += 1
+		if since == 2:
+			sch.append(("fold",)); since = 0
+	return sch + [("fold",)]
+
+
+@pytest.mark.parametrize("depth", [16, 32, 48, 64, 80, 96, 112, 128, 144, 160, 256, 384, 400])
+def test_macro3_a16_schedule_matches_oracle(depth):
+	rows, rows3 = _table(), _table3()
+	g = np.random.RandomState(3000 + depth)
+	actions = g.randint(0, 12, (200, depth)).astype(np.uint8)
+	f, d = O.indices_to_actions(actions)
+	assert (_run_schedule(actions, rows, rows3, _schedule_a16(depth)) == O.scramble_many(f, d, True)).all()
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3, 4, 5, 11, 12, 13, 14, 23, 24, 25, 26, 47, 48, 49, 100, 101, 250])
+def test_seeded_schedule_on_the_seeded_stream_matches_oracle(depth):
+	"""The device-seeded kernel's row order and fold schedule, on the action stream the oracle's Philox restatement draws."""
+	rows, rows3 = _table(), _table3()
+	actions = O.seeded_actions(99 + depth, 5, 200, depth)
+	f, d = O.indices_to_actions(actions)
+	assert (_run_schedule(actions, rows, rows3, _schedule_seeded(depth)) == O.scramble_many(f, d, True)).all()
+	# worst case for the accumulators: every row adds 2 to some twist
+	worst = np.tile(np.array([0, 2, 4, 6, 8, 10], dtype=np.uint8), (4, depth // 6 + 1))[:, :depth]
+	f, d = O.indices_to_actions(worst)
+	assert (_run_schedule(worst, rows, rows3, _schedule_seeded(depth)) == O.scramble_many(f, d, True)).all()
+
+
 def test_macro_table_rows_are_permutations():
 	rows = _table()
 	sc = rows[:, 0]
