@@ -399,6 +399,7 @@ def run_gpu(args):
 	cpu_chunks = 12 if cpu_kind == "reference" else 32     # ~8-10 s of work on every host core
 	cpu_value, cpu_dt = cpu_scramble_throughput(cpu_chunks, depth, cores, cpu_kind)
 	port_value, port_dt = cpu_scramble_throughput(16, depth, cores, "port")
+	one_value, one_dt = cpu_scramble_throughput(4, depth, 1, cpu_kind)          # the reference as it runs: one process
 	ncu_per_cube, limiter, ncu_src = ncu_capture()
 	result = {
 		"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -414,12 +415,16 @@ def run_gpu(args):
 					 "note": "100 dependent moves per 120 bytes: the multi-move scramble is instruction-bound (integer ALU + heavy-FMA issue), not HBM-bound: DESIGN.md 3.1",
 					 "limiter": dict(limiter, source=ncu_src) if limiter else None},
 		"cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": cpu_kind, "sample": cpu_sample_text(cpu_kind, cores, cpu_chunks, depth, cpu_dt),
+						 "single_process": {"value": one_value, "cores": 1, "kind": cpu_kind, "sample": cpu_sample_text(cpu_kind, 1, 4, depth, one_dt)},
 						 "port": {"value": port_value, "kind": "port", "sample": cpu_sample_text("port", cores, 16, depth, port_dt)}},
 		"e2e": {"value": world * n * depth / seeded_s, "unit": UNIT, "h2d_bytes_per_step": 16, "d2h_bytes_per_step": n * 20,
 				"ms_per_step": seeded_s * 1e3, "parity_ok": seeded_ok,
 				"api": "rbh_scramble_seeded (C ABI): the moves are drawn on the device (Philox4x32-10, one subsequence per cube) as cube.scramble "
 					   "draws its own (cube.py:206-211); in: seed + first cube id (16 B), out: int8[n][20] to pinned host memory",
 				"algorithmic_bytes_per_cube": 20,
+				"note": "PCIe-bound: 20 B per cube come back at ~56 GB/s on one GPU; the N GPUs of one box share one path into host memory "
+						"(71 / 75 / 95 GB/s in total at N = 2 / 4 / 8 on this pool's VM hosts, DESIGN.md 6), so the end-to-end rate does not scale with N "
+						"while the device-timed value does",
 				"host_actions": {"value": world * n * depth / host_s, "ms_per_step": host_s * 1e3, "h2d_bytes_per_step": n * depth,
 								 "d2h_bytes_per_step": n * 20, "api": "rbh_scramble: host-drawn uint8[n][100] actions in", "parity_ok": e2e_ok,
 								 "algorithmic_bytes_per_cube": 120},

@@ -126,6 +126,30 @@ def sharded_scramble(actions, gather: bool = True):
 	return sharded_apply(cube.scramble_batch, actions, gather=gather, device=dev)
 
 
+def seeded_shard(n_total: int) -> tuple[int, int]:
+	"""(first_cube, count) of this rank's share of a device-seeded scramble of `n_total` cubes.  The cube id is the Philox
+	subsequence (`rb_scramble_seeded`), so the union of the ranks' results is the single-GPU result whatever the world size."""
+	rank, ws = world()
+	lo, hi = shard_bounds(n_total, ws, rank)
+	return lo, hi - lo
+
+
+def sharded_scramble_seeded(n_total: int, depth: int, seed: int, gather: bool = False, scramble=None):
+	"""`cube.scramble_seeded` over all ranks: rank r draws and scrambles cubes [lo_r, hi_r) of ONE stream; no collective unless
+	`gather`.  `scramble(count, depth, seed, first_cube)` defaults to the CUDA path (the CPU tests pass a stand-in)."""
+	if scramble is None:
+		from . import cube
+		scramble = cube.scramble_seeded
+	first, count = seeded_shard(n_total)
+	local = scramble(count, depth, seed, first)
+	if not gather:
+		return local
+	was_np = isinstance(local, np.ndarray)
+	t = torch.from_numpy(np.ascontiguousarray(local)) if was_np else local
+	out = gather_rows(t, n_total)
+	return out.cpu().numpy() if was_np else out
+
+
 def sharded_adi_generator(games: int, depth: int, reward_method: str = "lapanfix", **kw):
 	"""ADIGenerator for this rank's share of `games` (each rank then draws its own actions with rank_seed, runs its own
 	net replica and keeps its batch shard for data-parallel training)."""

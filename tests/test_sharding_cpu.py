@@ -117,3 +117,38 @@ def test_two_rank_gradient_mean_equals_full_batch_gradient():
 		for a, b in zip(ret[r], want):
 			np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-7)
 	S.allreduce_mean_([torch.ones(3)])                                  # no process group: no-op
+
+
+def _seeded_worker(rank, ws, port, n, depth, seed, ret):
+	os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws))
+	dist.init_process_group("gloo", rank=rank, world_size=ws)
+	try:
+		from oracle import cube_oracle as O
+
+		def scramble(count, depth, seed, first):                         # the oracle's restatement of the seeded kernel's stream
+			f, d = O.indices_to_actions(O.seeded_actions(seed, first, count, depth))
+			return O.scramble_many(f, d, True) if count else np.zeros((0, 20), np.int8)
+
+		ret[rank] = dict(shard=S.seeded_shard(n), full=S.sharded_scramble_seeded(n, depth, seed, gather=True, scramble=scramble),
+						 local=S.sharded_scramble_seeded(n, depth, seed, scramble=scramble))
+	finally:
+		dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [10, 33])
+def test_two_rank_seeded_scramble_is_one_stream(n):
+	"""Device-seeded scramble under sharding: cube id = Philox subsequence, so two ranks together produce exactly what one rank
+	produces for the whole range (host logic; the stream comes from the oracle's restatement here, from the kernel on the GPU)."""
+	from oracle import cube_oracle as O
+	depth, seed, ws = 17, 4242, 2
+	mgr = mp.Manager()
+	ret = mgr.dict()
+	mp.spawn(_seeded_worker, args=(ws, _free_port(), n, depth, seed, ret), nprocs=ws, join=True)
+	f, d = O.indices_to_actions(O.seeded_actions(seed, 0, n, depth))
+	want = O.scramble_many(f, d, True)
+	firsts = [ret[r]["shard"] for r in range(ws)]
+	assert firsts[0][0] == 0 and firsts[1][0] == firsts[0][1] and firsts[0][1] + firsts[1][1] == n
+	for r in range(ws):
+		assert (ret[r]["full"] == want).all()
+		lo, cnt = firsts[r]
+		assert (ret[r]["local"] == want[lo:lo + cnt]).all()
