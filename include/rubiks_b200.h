@@ -256,6 +256,10 @@ int rbh_scramble_seeded(int rep, uint64_t seed, uint64_t first_cube, int8_t* out
 /* multi_rotate on host buffers (the reference's own call shape: numpy in, numpy out). */
 int rbh_multi_rotate(int rep, const int8_t* states, const uint8_t* faces, const uint8_t* dirs,
                      int8_t* out, int64_t n);
+/* Pinned host buffers for the rbh_* calls (optional: any host pointer works, pinned ones copy asynchronously).  huge != 0 asks
+ * for transparent huge pages before pinning.  NULL on failure (rb_last_error). */
+void* rbh_host_alloc(int64_t bytes, int huge);
+int   rbh_host_free(void* ptr, int64_t bytes);
 /* Release cached device staging buffers held by the rbh_* entry points. */
 int rbh_release(void);
 

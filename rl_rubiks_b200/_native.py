@@ -73,6 +73,8 @@ SIGNATURES = {
 	"rbh_scramble_packed": (C.c_int, [C.c_int, _p, _p, _i64, _i32]),
 	"rbh_scramble_seeded": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, _p, _i64, _i32]),
 	"rbh_multi_rotate": (C.c_int, [C.c_int, _p, _p, _p, _p, _i64]),
+	"rbh_host_alloc": (_p, [_i64, C.c_int]),
+	"rbh_host_free": (C.c_int, [_p, _i64]),
 	"rbh_release": (C.c_int, []),
 }
 

@@ -1,4 +1,5 @@
 // librubiks_b200.so -- C ABI (include/rubiks_b200.h) over the sm_100a kernels.  Single translation unit.
+#include <sys/mman.h>
 #include "rb_common.cuh"
 #include "rb_tables.cuh"
 #include "rb_cube2024.cuh"
@@ -787,6 +788,33 @@ int rbh_multi_rotate(int rep, const int8_t* states, const uint8_t* faces, const 
 		RB_CUDA(cudaMemcpyAsync(out + base * sb, st.buf[k][2], (size_t)cnt * sb, cudaMemcpyDeviceToHost, s));
 		return RB_OK;
 	});
+}
+
+// Pinned host memory for the rbh_* calls.  huge != 0: anonymous mapping advised to transparent huge pages before it is touched
+// and registered (2 MB pages keep the IOMMU / DMA translation working set of a multi-GB transfer small; several GPUs copying
+// at once into 4 KB-paged buffers are translation-bound on some hosts).  Free with rbh_host_free(ptr, bytes).
+void* rbh_host_alloc(int64_t bytes, int huge) {
+	if (bytes <= 0) return nullptr;
+	const size_t sz = ((size_t)bytes + (2u << 20) - 1) & ~((size_t)(2u << 20) - 1);
+	void* p = mmap(nullptr, sz, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+	if (p == MAP_FAILED) { rb_fail(RB_ERR_BAD_ARG, "mmap of the host buffer failed%s%s"); return nullptr; }
+	if (huge) madvise(p, sz, MADV_HUGEPAGE);
+	memset(p, 0, sz);                                      // touch: pages (huge ones where the kernel grants them) exist before pinning
+	if (cudaHostRegister(p, sz, cudaHostRegisterPortable) != cudaSuccess) {
+		cudaGetLastError();
+		munmap(p, sz);
+		rb_fail(RB_ERR_CUDA, "cudaHostRegister of the host buffer failed%s%s");
+		return nullptr;
+	}
+	return p;
+}
+
+int rbh_host_free(void* ptr, int64_t bytes) {
+	if (!ptr) return RB_OK;
+	const size_t sz = ((size_t)bytes + (2u << 20) - 1) & ~((size_t)(2u << 20) - 1);
+	RB_CUDA(cudaHostUnregister(ptr));
+	munmap(ptr, sz);
+	return RB_OK;
 }
 
 int rbh_release(void) {
