@@ -174,12 +174,16 @@ k_scramble_seeded(PhiloxKeys keys, uint64_t first_cube, int8_t* __restrict__ out
 static int launch_seeded(uint64_t seed, uint64_t first_cube, int8_t* out, int64_t n, int depth, cudaStream_t st, int out_pitch = 20) {
 	int rc = ensure_device();
 	if (rc != RB_OK) return rc;
-	static bool attr_done[64] = {};
-	int dev = 0;
-	RB_CUDA(cudaGetDevice(&dev));
-	if (!attr_done[dev]) {
-		RB_CUDA(cudaFuncSetAttribute(k_scramble_seeded, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeedSmem));
-		attr_done[dev] = true;
+	{
+		static std::mutex mu;
+		static bool attr_done[64] = {};
+		int dev = 0;
+		RB_CUDA(cudaGetDevice(&dev));
+		std::lock_guard<std::mutex> lock(mu);
+		if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+			RB_CUDA(cudaFuncSetAttribute(k_scramble_seeded, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeedSmem));
+			attr_done[dev] = true;
+		}
 	}
 	const int64_t chunks = (n + 31) / 32;
 	int64_t warps = (chunks + RB_NUM_SMS - 1) / RB_NUM_SMS;                 // small n: one chunk per warp on as many SMs as possible
