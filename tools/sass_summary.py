@@ -13,7 +13,7 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "rl_rubiks_b200", "librubiks_b200.so")
 PATTERNS = [("UBLKCP", r"\bUBLKCP"), ("UTMALDG", r"\bUTMALDG"), ("SYNCS", r"\bSYNCS"), ("ATOMG.CAS.128", r"ATOMG\.E\.CAS\.128"), ("ATOMG", r"\bATOMG"),
-			("REDG", r"\bREDG"), ("PRMT", r"\bPRMT"), ("IDP.4A", r"\bIDP\.4A"), ("LOP3", r"\bLOP3"), ("IMAD.HI", r"\bIMAD\.HI"), ("LDS.128", r"\bLDS\.128"),
+			("REDG", r"\bREDG"), ("PRMT", r"\bPRMT"), ("IDP.4A", r"\bIDP\.4A"), ("IDP.2A", r"\bIDP\.2A"), ("LOP3", r"\bLOP3"), ("IMAD.HI", r"\bIMAD\.HI"), ("LDS.128", r"\bLDS\.128"),
 			("LDS", r"\bLDS\b"), ("STG.128", r"\bSTG\.E\.(EF\.)?128"), ("LDG.128", r"\bLDG\.E\.(\w+\.)*128"), ("SHFL", r"\bSHFL"), ("BAR", r"\bBAR\.")]
 
 
