@@ -64,22 +64,23 @@ def main():
 		dist.init_process_group("nccl", device_id=dev)
 	torch.backends.cuda.matmul.allow_tf32 = args.tf32
 	torch.manual_seed(0)                                                  # same replica on every rank
-	np.random.seed(sharding.rank_seed(0, rank))                           # own scrambles on every rank
+	np.random.seed(0)                                                     # one global numpy stream; Train derives a per-rank draw stream from it
 	net = FcSmall().to(dev)
 	lo, hi = sharding.shard_bounds(args.games, world, rank)
 	games = hi - lo
 
 	# (a) generation alone: kernels + value-net forward + targets
 	g = adi.ADIGenerator(games, args.depth, "lapanfix", oh_dtype=oh_dtype)
+	rng = np.random.RandomState(sharding.rank_seed(0, rank))              # own scrambles on every rank
 	cast = torch.autocast("cuda", dtype=torch.bfloat16, enabled=args.bf16)
 	for _ in range(2):
 		with cast:
-			adi.adi_traindata(net, games, args.depth, "lapanfix", 0.5, ff_batches=args.ff_batches, generator=g)
+			adi.adi_traindata(net, games, args.depth, "lapanfix", 0.5, ff_batches=args.ff_batches, generator=g, rng=rng)
 	torch.cuda.synchronize()
 	t0 = time.perf_counter()
 	for _ in range(args.rollouts):
 		with cast:
-			adi.adi_traindata(net, games, args.depth, "lapanfix", 0.5, ff_batches=args.ff_batches, generator=g)
+			adi.adi_traindata(net, games, args.depth, "lapanfix", 0.5, ff_batches=args.ff_batches, generator=g, rng=rng)
 	torch.cuda.synchronize()
 	gen_s = (time.perf_counter() - t0) / args.rollouts
 	# kernels only (no net): generate + targets on stale values
@@ -93,7 +94,8 @@ def main():
 	del g, vals
 
 	# (b) the whole loop: generation + SGD over the rollout's minibatches
-	t = Train(rollouts=args.rollouts + 1, batch_size=args.batch, rollout_games=games, rollout_depth=args.depth, optim_fn=torch.optim.Adam,
+	# Train shards `rollout_games` over the ranks itself when data_parallel is set
+	t = Train(rollouts=args.rollouts + 1, batch_size=args.batch, rollout_games=args.games, rollout_depth=args.depth, optim_fn=torch.optim.Adam,
 			  alpha_update=0.5, lr=1e-5, gamma=1, update_interval=1, tau=1, reward_method="lapanfix", data_parallel=world > 1, oh_dtype=oh_dtype)
 	t.adi_ff_batches = args.ff_batches
 	marks = []
