@@ -110,22 +110,37 @@ class Train:
 		"""One pass over a rollout's batch in minibatches (train.py:165-179): loss = mean((CE + MSE) * loss_weights); the two
 		per-minibatch loss means are accumulated in f64 on the device (one host read per rollout instead of one per minibatch)."""
 		oh, policy_t, value_t, weights = batch
-		bounds = self._get_batches(oh.shape[0], self.batch_size)
+		rank, ws = sharding.world() if self.data_parallel else (0, 1)
+		if ws == 1:
+			bounds = self._get_batches(oh.shape[0], self.batch_size)
+		else:
+			# every rank must run the same number of minibatches (one gradient all-reduce each) although shards may differ by a
+			# game: the count is taken from the largest shard, the rank's own states are cut into that many near-equal slices; the
+			# unused shuffle consumes the global numpy stream for the WHOLE rollout's size, identically on every rank
+			np.random.shuffle(np.arange(self.rollout_games * self.rollout_depth))
+			largest = -(-self.rollout_games // ws) * self.rollout_depth
+			nb = max(1, -(-largest // self.batch_size))
+			edges = [oh.shape[0] * k // nb for k in range(nb + 1)]
+			bounds = [slice(edges[k], edges[k + 1]) for k in range(nb)]
 		acc.zero_()
 		net.train()
 		for sl in bounds:
 			optimizer.zero_grad()
-			with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.oh_dtype == torch.bfloat16):
-				policy_pred, value_pred = net(oh[sl], policy=True, value=True)
-			w = weights[sl]
-			policy_loss = self.policy_criterion(policy_pred.float(), policy_t[sl]) * w
-			value_loss = self.value_criterion(value_pred.float().squeeze(), value_t[sl]) * w
-			torch.mean(policy_loss + value_loss).backward()
+			if sl.stop > sl.start:
+				with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.oh_dtype == torch.bfloat16):
+					policy_pred, value_pred = net(oh[sl], policy=True, value=True)
+				w = weights[sl]
+				policy_loss = self.policy_criterion(policy_pred.float(), policy_t[sl]) * w
+				value_loss = self.value_criterion(value_pred.float().squeeze(), value_t[sl]) * w
+				torch.mean(policy_loss + value_loss).backward()
+				acc[0] += policy_loss.detach().mean().double() / len(bounds)
+				acc[1] += value_loss.detach().mean().double() / len(bounds)
+			else:                                            # fewer states than minibatches on this rank: it joins the exchange with zeros
+				for p in params:
+					p.grad = torch.zeros_like(p)
 			if self.data_parallel:
 				sharding.allreduce_mean_([p.grad for p in params if p.grad is not None])
 			optimizer.step()
-			acc[0] += policy_loss.detach().mean().double() / len(bounds)
-			acc[1] += value_loss.detach().mean().double() / len(bounds)
 		return acc.tolist()
 
 	def train(self, net):
