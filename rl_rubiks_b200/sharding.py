@@ -126,6 +126,17 @@ def sharded_scramble(actions, gather: bool = True):
 	return sharded_apply(cube.scramble_batch, actions, gather=gather, device=dev)
 
 
+def dp_minibatch_bounds(own_states: int, games: int, depth: int, batch_size: int, world_size: int) -> list:
+	"""Minibatch slices of one rank's share of a rollout in data-parallel training.  Every rank must run the same number of
+	minibatches (one gradient all-reduce each) although shards may differ by one game: the count comes from the largest
+	shard (ceil(games / world) * depth states at `batch_size` per minibatch), the rank's own states are cut into that many
+	near-equal contiguous slices (possibly empty ones on a rank with fewer states than minibatches)."""
+	largest = -(-int(games) // world_size) * int(depth)
+	nb = max(1, -(-largest // int(batch_size)))
+	edges = [own_states * k // nb for k in range(nb + 1)]
+	return [slice(edges[k], edges[k + 1]) for k in range(nb)]
+
+
 def seeded_shard(n_total: int) -> tuple[int, int]:
 	"""(first_cube, count) of this rank's share of a device-seeded scramble of `n_total` cubes.  The cube id is the Philox
 	subsequence (`rb_scramble_seeded`), so the union of the ranks' results is the single-GPU result whatever the world size."""

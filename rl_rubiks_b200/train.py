@@ -118,10 +118,7 @@ class Train:
 			# game: the count is taken from the largest shard, the rank's own states are cut into that many near-equal slices; the
 			# unused shuffle consumes the global numpy stream for the WHOLE rollout's size, identically on every rank
 			np.random.shuffle(np.arange(self.rollout_games * self.rollout_depth))
-			largest = -(-self.rollout_games // ws) * self.rollout_depth
-			nb = max(1, -(-largest // self.batch_size))
-			edges = [oh.shape[0] * k // nb for k in range(nb + 1)]
-			bounds = [slice(edges[k], edges[k + 1]) for k in range(nb)]
+			bounds = sharding.dp_minibatch_bounds(oh.shape[0], self.rollout_games, self.rollout_depth, self.batch_size, ws)
 		acc.zero_()
 		net.train()
 		for sl in bounds:

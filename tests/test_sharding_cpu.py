@@ -31,6 +31,21 @@ def test_shard_bounds_partition_every_unit_once():
 	assert len({S.rank_seed(0, r) for r in range(8)}) == 8
 
 
+def test_dp_minibatch_bounds_agree_across_ranks():
+	"""Data-parallel training: every rank runs the same number of minibatches whatever its shard size, and its slices cover its
+	states exactly once, in order."""
+	for games, depth, bsize, ws in ((7501, 30, 1000, 2), (7, 30, 100, 2), (3, 5, 4, 8), (1000, 25, 25000, 4), (9, 2, 1, 4)):
+		counts = set()
+		for r in range(ws):
+			lo, hi = S.shard_bounds(games, ws, r)
+			own = (hi - lo) * depth
+			b = S.dp_minibatch_bounds(own, games, depth, bsize, ws)
+			counts.add(len(b))
+			assert b[0].start == 0 and b[-1].stop == own and all(b[k].stop == b[k + 1].start for k in range(len(b) - 1))
+			assert max(x.stop - x.start for x in b) <= bsize
+		assert len(counts) == 1
+
+
 def test_single_process_is_identity():
 	x = torch.arange(12).reshape(6, 2)
 	assert S.world() == (0, 1)
