@@ -21,31 +21,28 @@ k_check_range(int rep, const uint8_t* __restrict__ states, int64_t n_state_bytes
 
 // Packed actions -> action bytes.  Packed byte p = a0 + 13 * a1 holds moves (2k, 2k + 1) of a cube (a1 = 12: no second move, only
 // in the last byte of an odd-depth row) -- the row index of the 2-move table (rb_get_macro_table).  Rows: packed [n][(depth + 1) / 2],
-// actions [n][depth].  Even depth is one flat stream: 16 packed bytes in, 32 action bytes out per thread.
+// actions [n][depth].  Even depth is one flat stream: 8 packed bytes in, 16 action bytes out per thread.
 __global__ void __launch_bounds__(256)
 k_unpack_actions(const uint8_t* __restrict__ packed, uint8_t* __restrict__ actions, int64_t n, int depth, int vec_ok) {
 	const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const int pb = (depth + 1) >> 1;
-	auto split = [](uint32_t w, uint32_t& lo, uint32_t& hi) {                 // 4 packed bytes -> 8 action bytes
-		uint32_t a[8];
-#pragma unroll
-		for (int k = 0; k < 4; ++k) {
-			const uint32_t p = (w >> (8 * k)) & 0xffu, q = (p * 79u) >> 10;     // p / 13 for p < 256
-			a[2 * k] = p - 13u * q; a[2 * k + 1] = q;
-		}
-		lo = a[0] | (a[1] << 8) | (a[2] << 16) | (a[3] << 24);
-		hi = a[4] | (a[5] << 8) | (a[6] << 16) | (a[7] << 24);
+	auto split = [](uint32_t w, uint32_t& lo, uint32_t& hi) {                 // 4 packed bytes -> 8 action bytes, two bytes per 16-bit lane
+		const uint32_t ev = w & 0x00ff00ffu, od = (w >> 8) & 0x00ff00ffu;      // packed bytes (0, 2) and (1, 3)
+		const uint32_t qe = ((ev * 79u) >> 10) & 0x003f003fu, qo = ((od * 79u) >> 10) & 0x003f003fu;   // p / 13 per lane (p * 79 < 2^16: no carry across lanes)
+		const uint32_t pe = ev - 13u * qe + (qe << 8), po = od - 13u * qo + (qo << 8);                 // lanes (a, q): the two moves of a packed byte
+		asm("prmt.b32 %0, %1, %2, 0x5410;" : "=r"(lo) : "r"(pe), "r"(po));    // moves of packed bytes 0, 1
+		asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(hi) : "r"(pe), "r"(po));    // moves of packed bytes 2, 3
 	};
 	if (vec_ok) {                                                            // even depth, 16-byte aligned pointers
-		const int64_t total = n * pb, nv = total >> 4;
+		// 8 packed bytes in, 16 action bytes out per thread: both the loads (256 B per warp) and the stores (512 B) are contiguous
+		const int64_t total = n * pb, nv = total >> 3;
 		for (int64_t i = t0; i < nv; i += stride) {
-			const uint4 v = rb_ld_stream(reinterpret_cast<const uint4*>(packed) + i);
-			uint4 o0, o1;
-			split(v.x, o0.x, o0.y); split(v.y, o0.z, o0.w); split(v.z, o1.x, o1.y); split(v.w, o1.z, o1.w);
-			reinterpret_cast<uint4*>(actions)[2 * i] = o0;
-			reinterpret_cast<uint4*>(actions)[2 * i + 1] = o1;
+			const uint2 v = __ldcs(reinterpret_cast<const uint2*>(packed) + i);
+			uint4 o;
+			split(v.x, o.x, o.y); split(v.y, o.z, o.w);
+			__stcs(reinterpret_cast<uint4*>(actions) + i, o);
 		}
-		for (int64_t i = (nv << 4) + t0; i < total; i += stride) {
+		for (int64_t i = (nv << 3) + t0; i < total; i += stride) {
 			const uint32_t p = packed[i], q = (p * 79u) >> 10;
 			actions[2 * i] = (uint8_t)(p - 13u * q); actions[2 * i + 1] = (uint8_t)q;
 		}

@@ -686,7 +686,7 @@ int rb_unpack_actions(const uint8_t* packed, uint8_t* actions, int64_t n, int32_
 	RB_REQUIRE(packed && actions, "null pointer");
 	const int vec_ok = depth % 2 == 0 && aligned(packed, 16) && aligned(actions, 16);
 	const int64_t work = n * ((depth + 1) / 2);
-	rbh::k_unpack_actions<<<rb_grid(vec_ok ? work / 16 + 1 : work, 256, 8), 256, 0, S(stream)>>>(packed, actions, n, depth, vec_ok);
+	rbh::k_unpack_actions<<<rb_grid(vec_ok ? work / 8 + 1 : work, 256, 8), 256, 0, S(stream)>>>(packed, actions, n, depth, vec_ok);
 	RB_LAUNCHED("unpack_actions");
 	return RB_OK;
 }
