@@ -19,7 +19,7 @@ for rep in range(3):
 	e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 	t0 = time.perf_counter()
 	e0.record()
-	counts, hs = frontier.bfs_layers(depth, is2024=is2024, capacity=1 << 25 if is2024 else 1 << 22)
+	counts, hs = frontier.bfs_layers(depth, is2024=is2024, capacity=int(os.environ.get("BFS_CAP", str(1 << 25 if is2024 else 1 << 22))))
 	e1.record()
 	torch.cuda.synchronize()
 	dt = time.perf_counter() - t0
