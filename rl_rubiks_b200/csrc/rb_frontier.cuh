@@ -394,9 +394,9 @@ k_resolve(Provider prov, void* base, int64_t capacity, int64_t n, int need_first
 	if (index) index[i] = idx;
 	if (new_items) new_items[k] = (int32_t)i;
 	if (kFrontier) {
-		uint32_t w[5];
-		prov.load(i, s_lut, w);
 		const uint32_t u = (uint32_t)i, par = u / 12u;
+		uint32_t w[5] = {0u, 0u, 0u, 0u, 0u};
+		if (next_frontier || solved) prov.load(i, s_lut, w);                    // the state itself is regenerated only when somebody wants it
 		if (next_frontier) {
 			uint32_t* dst = reinterpret_cast<uint32_t*>(next_frontier + k * 20);     // 20 B records: 4-byte aligned
 #pragma unroll

@@ -113,15 +113,18 @@ class StateHashSet:
 		N.check(N.lib.rb_hashset_lookup(self.rep, N.ptr(self.table), self.capacity, N.ptr(s), n, N.ptr(index), N.ptr(scratch), N.stream_handle()))
 		return index.cpu().numpy() if was_np else index
 
-	def expand(self, frontier: torch.Tensor, flags: bool = False, parents: bool = True, solved: bool = True, index: bool = False):
+	def expand(self, frontier: torch.Tensor, flags: bool = False, parents: bool = True, solved: bool = True, index: bool = False,
+			   states: bool = True):
 		"""One frontier step: 12 children of every frontier state, dedup against the set and within the batch, new states
 		compacted in batch order.  Returns a dict of device tensors sized for the worst case (12 n rows); the first
-		`n_new` rows are valid.  `n_new` itself stays on the device (`out['n_new']`) until the caller reads it."""
+		`n_new` rows are valid.  `n_new` itself stays on the device (`out['n_new']`) until the caller reads it.
+		`states=False` (20x24 only): the new states are counted and entered into the set but not written out (the last layer of
+		a closure)."""
 		f, _ = self._states(frontier)
 		n = f.shape[0]
 		m = 12 * n
 		self._reserve(m)
-		out = {"next": torch.empty(m, *self.shape, dtype=torch.int8, device=self.dev)}
+		out = {"next": torch.empty(m, *self.shape, dtype=torch.int8, device=self.dev) if states or not self.is2024 else None}
 		out["parent"] = torch.empty(m, dtype=torch.int32, device=self.dev) if parents else None
 		out["action"] = torch.empty(m, dtype=torch.uint8, device=self.dev) if parents else None
 		out["solved"] = torch.empty(m, dtype=torch.uint8, device=self.dev) if solved else None
@@ -153,10 +156,11 @@ def bfs_layers(max_depth: int, start=None, is2024: bool | None = None, capacity:
 	events = [torch.cuda.Event(enable_timing=True) for _ in range(max_depth + 1)]
 	events[0].record()
 	for d in range(max_depth):
-		out = hs.expand(frontier, parents=False, solved=False)
+		last = d == max_depth - 1                    # nobody expands the last layer's states: they are entered into the set and counted only
+		out = hs.expand(frontier, parents=False, solved=False, states=not last)
 		events[d + 1].record()
 		n_new = read_count(out["n_new"])
-		frontier = out["next"][:n_new]
+		frontier = out["next"][:n_new] if out["next"] is not None else None
 		counts.append(n_new)
 	global LAST_LAYER_MS
 	LAST_LAYER_MS = [events[d].elapsed_time(events[d + 1]) for d in range(max_depth)]      # device time per layer (diagnostics)
