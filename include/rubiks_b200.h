@@ -208,6 +208,17 @@ int rb_frontier_expand(int rep, void* table, int64_t capacity, const int8_t* fro
                        int32_t* count_dev, int8_t* next_frontier, int32_t* parent, uint8_t* action,
                        uint8_t* solved, uint8_t* seen, uint8_t* first, int32_t* index, int32_t* n_new_dev,
                        void* scratch, rb_stream_t stream);
+/* The same with the frontier's size on the DEVICE: frontier holds *n_dev (<= n_max) states; buffers and scratch are sized for
+ * n_max.  Lets a caller enqueue consecutive layers (n_dev of layer d+1 = n_new_dev of layer d) without a host round trip while
+ * the upper bound 12^d is small.  20x24 representation; no per-item seen / first / index outputs. */
+int rb_frontier_expand_dev(int rep, void* table, int64_t capacity, const int8_t* frontier, int64_t n_max, const int32_t* n_dev,
+                           int32_t* count_dev, int8_t* next_frontier, int32_t* parent, uint8_t* action, uint8_t* solved,
+                           int32_t* n_new_dev, void* scratch, rb_stream_t stream);
+/* `layers` consecutive rb_frontier_expand_dev calls enqueued by one host call: layer d reads its frontier from buf_a (d even) or
+ * buf_b (d odd) and writes the next one into the other; sizes_dev[0] = n0 on entry, sizes_dev[d + 1] receives the number of new
+ * states of layer d.  Buffers hold n0 * 12^layers states, scratch is rb_frontier_scratch_bytes(rep, n0 * 12^(layers-1)). */
+int rb_frontier_expand_chain(int rep, void* table, int64_t capacity, int8_t* buf_a, int8_t* buf_b, int64_t n0, int32_t layers,
+                             int32_t* sizes_dev, int32_t* count_dev, void* scratch, rb_stream_t stream);
 int64_t rb_frontier_scratch_bytes(int rep, int64_t n);
 
 /* ---- batched weighted A* on the device (agents.py:221-367 for K cubes at once; 20x24 representation) -----------------

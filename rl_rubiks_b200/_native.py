@@ -59,6 +59,8 @@ SIGNATURES = {
 	"rb_hashset_insert_unique": (C.c_int, [C.c_int, _p, _i64, _p, _i64, _p, _p, _p, _p, _p, _p]),
 	"rb_hashset_lookup": (C.c_int, [C.c_int, _p, _i64, _p, _i64, _p, _p, _p]),
 	"rb_frontier_expand": (C.c_int, [C.c_int, _p, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+	"rb_frontier_expand_dev": (C.c_int, [C.c_int, _p, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+	"rb_frontier_expand_chain": (C.c_int, [C.c_int, _p, _i64, _p, _p, _i64, _i32, _p, _p, _p, _p]),
 	"rb_frontier_scratch_bytes": (_i64, [C.c_int, _i64]),
 	"rb_astar_scratch_bytes": (_i64, [_i32, _i32]),
 	"rb_astar_init": (C.c_int, [_p, _p, _p]),

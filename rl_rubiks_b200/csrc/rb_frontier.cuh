@@ -237,10 +237,13 @@ __device__ __forceinline__ void probe_item(const Table& t, Key k, int64_t i, boo
 template <class Provider>
 __global__ void __launch_bounds__(kThreads)
 k_probe2024(Provider prov, void* base, int64_t capacity, int64_t n, int need_first, uint32_t* __restrict__ word, uint8_t* lost,
-            uint32_t* __restrict__ ctl, uint8_t* __restrict__ seen, int32_t* __restrict__ index) {
+            uint32_t* __restrict__ ctl, uint8_t* __restrict__ seen, int32_t* __restrict__ index, const int32_t* __restrict__ n_units_dev, int per_unit) {
+	// n_units_dev != nullptr: the batch really holds per_unit * *n_units_dev items (<= n, the size the grid was launched for): lets a
+	// caller chain batches whose size is only known on the device (the layers of a BFS) without a host round trip
 	__shared__ __align__(16) uint8_t s_lut[RB_LUT_BYTES];
 	rb_stage_lut2024(s_lut);
 	__syncthreads();
+	if (n_units_dev) n = min(n, (int64_t)per_unit * (int64_t)*n_units_dev);
 	const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
 	if (i >= n) return;
 	uint32_t w[5];
@@ -349,7 +352,7 @@ __global__ void __launch_bounds__(kThreads)
 k_resolve(Provider prov, void* base, int64_t capacity, int64_t n, int need_first, const uint32_t* __restrict__ word,
           const uint8_t* __restrict__ lost, unsigned long long* __restrict__ status, uint32_t* __restrict__ ctl, int32_t* __restrict__ count, int32_t* __restrict__ n_new,
           uint8_t* __restrict__ first, int32_t* __restrict__ index, int32_t* __restrict__ new_items, int8_t* __restrict__ next_frontier,
-          int32_t* __restrict__ parent, uint8_t* __restrict__ action, uint8_t* __restrict__ solved) {
+          int32_t* __restrict__ parent, uint8_t* __restrict__ action, uint8_t* __restrict__ solved, const int32_t* __restrict__ n_units_dev, int per_unit) {
 	__shared__ __align__(16) uint8_t s_lut[RB_LUT_BYTES];
 	__shared__ int32_t s_warp[kThreads / 32];
 	__shared__ int32_t s_bid, s_excl, s_count;
@@ -359,6 +362,8 @@ k_resolve(Provider prov, void* base, int64_t capacity, int64_t n, int need_first
 	const int32_t b = s_bid;
 	const Table t = table_of(base, capacity);
 	const int64_t i = (int64_t)b * kThreads + threadIdx.x;
+	const int64_t n_launched = n;                                             // the grid covers this many items; fewer may exist (n_units_dev)
+	if (n_units_dev) n = min(n, (int64_t)per_unit * (int64_t)*n_units_dev);
 	uint32_t wd = kNoSlot;
 	bool fs = false, is_new = false;
 	if (i < n) {
@@ -377,7 +382,7 @@ k_resolve(Provider prov, void* base, int64_t capacity, int64_t n, int need_first
 		const int32_t excl = lookback(status, b, agg);                            // rewrites count only after every block has read it
 		if (threadIdx.x == 0) {
 			s_excl = excl; s_count = c0;
-			if ((int64_t)b == (n + kThreads - 1) / kThreads - 1) {
+			if ((int64_t)b == (n_launched + kThreads - 1) / kThreads - 1) {
 				const bool bad = c0 < 0 || *reinterpret_cast<volatile uint32_t*>(ctl + 1) != 0;
 				*count = bad ? -1 : c0 + excl + agg;
 				if (n_new) *n_new = bad ? -1 : excl + agg;

@@ -416,7 +416,7 @@ int rb_hashset_insert_unique(int rep, void* table, int64_t capacity, const int8_
 	RB_CUDA(cudaMemsetAsync(sc.lost, 0, (size_t)rbf::control_bytes(n), st));
 	const int need_first = first != nullptr;
 	if (rep == RB_REP_2024) {
-		rbf::k_probe2024<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(rbf::FromArray2024{states}, table, capacity, n, need_first, sc.word, sc.lost, sc.ctl, seen, index);
+		rbf::k_probe2024<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(rbf::FromArray2024{states}, table, capacity, n, need_first, sc.word, sc.lost, sc.ctl, seen, index, nullptr, 1);
 		RB_LAUNCHED("frontier_probe_2024");
 	} else {
 		RB_REQUIRE(aligned(states, 4), "6x8x6 states must be 4-byte aligned");
@@ -427,7 +427,7 @@ int rb_hashset_insert_unique(int rep, void* table, int64_t capacity, const int8_
 	}
 	rbf::k_resolve<rbf::NoProvider, false><<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(
 		rbf::NoProvider{}, table, capacity, n, need_first, sc.word, sc.lost, sc.status, sc.ctl, count_dev, nullptr, first, index, nullptr, nullptr, nullptr,
-		nullptr, nullptr);
+		nullptr, nullptr, nullptr, 1);
 	RB_LAUNCHED("frontier_resolve");
 	if (index) {
 		rbf::k_index_rest<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(table, capacity, n, sc.word, first, index);
@@ -459,9 +459,9 @@ int rb_hashset_lookup(int rep, const void* table, int64_t capacity, const int8_t
 	return RB_OK;
 }
 
-int rb_frontier_expand(int rep, void* table, int64_t capacity, const int8_t* frontier, int64_t n, int32_t* count_dev,
-                       int8_t* next_frontier, int32_t* parent, uint8_t* action, uint8_t* solved, uint8_t* seen, uint8_t* first,
-                       int32_t* index, int32_t* n_new_dev, void* scratch, rb_stream_t stream) {
+static int frontier_expand_impl(int rep, void* table, int64_t capacity, const int8_t* frontier, int64_t n, const int32_t* n_dev, int32_t* count_dev,
+                                int8_t* next_frontier, int32_t* parent, uint8_t* action, uint8_t* solved, uint8_t* seen, uint8_t* first,
+                                int32_t* index, int32_t* n_new_dev, void* scratch, rb_stream_t stream) {
 	RB_REQUIRE(rep_ok(rep) && n >= 0 && 12 * n < (1ll << 31), "bad rep or size");
 	if (n == 0) {
 		if (n_new_dev) RB_CUDA(cudaMemsetAsync(n_new_dev, 0, sizeof(int32_t), S(stream)));
@@ -478,14 +478,15 @@ int rb_frontier_expand(int rep, void* table, int64_t capacity, const int8_t* fro
 	const int need_first = first != nullptr;
 	if (rep == RB_REP_2024) {
 		const rbf::FromParent2024 prov{frontier};
-		rbf::k_probe2024<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(prov, table, capacity, items, need_first, sc.word, sc.lost, sc.ctl, seen, index);
+		rbf::k_probe2024<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(prov, table, capacity, items, need_first, sc.word, sc.lost, sc.ctl, seen, index, n_dev, 12);
 		RB_LAUNCHED("frontier_probe_2024");
 		rbf::k_resolve<rbf::FromParent2024, true><<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(
 			prov, table, capacity, items, need_first, sc.word, sc.lost, sc.status, sc.ctl, count_dev, n_new_dev, first, index, nullptr, next_frontier, parent,
-			action, solved);
+			action, solved, n_dev, 12);
 		RB_LAUNCHED("frontier_resolve_2024");
 	} else {
 		RB_REQUIRE(aligned(frontier, 16) && aligned(next_frontier, 16), "6x8x6 states must be 16-byte aligned");
+		RB_REQUIRE(!n_dev, "a device-side frontier size is supported for the 20x24 representation only");
 		int8_t* children = reinterpret_cast<int8_t*>(sc.keys + items);
 		int32_t* new_items = reinterpret_cast<int32_t*>(children + items * 288);
 		int32_t* n_new = n_new_dev ? n_new_dev : reinterpret_cast<int32_t*>(sc.ctl + 2);
@@ -497,7 +498,7 @@ int rb_frontier_expand(int rep, void* table, int64_t capacity, const int8_t* fro
 		RB_LAUNCHED("frontier_probe_keys");
 		rbf::k_resolve<rbf::NoProvider, false><<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(
 			rbf::NoProvider{}, table, capacity, items, need_first, sc.word, sc.lost, sc.status, sc.ctl, count_dev, n_new, first, index, new_items, nullptr,
-			nullptr, nullptr, nullptr);
+			nullptr, nullptr, nullptr, nullptr, 1);
 		RB_LAUNCHED("frontier_resolve");
 		rbf::k_gather686<<<rb_grid(items, 8, 8), rbf::kThreads, 0, st>>>(children, new_items, n_new, next_frontier, parent, action, solved);
 		RB_LAUNCHED("frontier_gather_686");
@@ -505,6 +506,36 @@ int rb_frontier_expand(int rep, void* table, int64_t capacity, const int8_t* fro
 	if (index) {
 		rbf::k_index_rest<<<(unsigned)sc.nb, rbf::kThreads, 0, st>>>(table, capacity, items, sc.word, first, index);
 		RB_LAUNCHED("frontier_index_rest");
+	}
+	return RB_OK;
+}
+
+int rb_frontier_expand(int rep, void* table, int64_t capacity, const int8_t* frontier, int64_t n, int32_t* count_dev,
+                       int8_t* next_frontier, int32_t* parent, uint8_t* action, uint8_t* solved, uint8_t* seen, uint8_t* first,
+                       int32_t* index, int32_t* n_new_dev, void* scratch, rb_stream_t stream) {
+	return frontier_expand_impl(rep, table, capacity, frontier, n, nullptr, count_dev, next_frontier, parent, action, solved, seen, first, index,
+	                            n_new_dev, scratch, stream);
+}
+
+int rb_frontier_expand_dev(int rep, void* table, int64_t capacity, const int8_t* frontier, int64_t n_max, const int32_t* n_dev,
+                           int32_t* count_dev, int8_t* next_frontier, int32_t* parent, uint8_t* action, uint8_t* solved,
+                           int32_t* n_new_dev, void* scratch, rb_stream_t stream) {
+	RB_REQUIRE(n_dev, "null device-side frontier size");
+	return frontier_expand_impl(rep, table, capacity, frontier, n_max, n_dev, count_dev, next_frontier, parent, action, solved, nullptr, nullptr, nullptr,
+	                            n_new_dev, scratch, stream);
+}
+
+int rb_frontier_expand_chain(int rep, void* table, int64_t capacity, int8_t* buf_a, int8_t* buf_b, int64_t n0, int32_t layers,
+                             int32_t* sizes_dev, int32_t* count_dev, void* scratch, rb_stream_t stream) {
+	RB_REQUIRE(rep == RB_REP_2024 && n0 > 0 && layers >= 0 && layers <= 8, "20x24 representation, 1..8 layers");
+	RB_REQUIRE(buf_a && buf_b && sizes_dev, "null buffer");
+	int64_t bound = n0;
+	for (int d = 0; d < layers; ++d) {
+		RB_REQUIRE(12 * bound < (1ll << 28), "chained layers are for small frontiers (upper bound 12^d)");
+		int rc = frontier_expand_impl(rep, table, capacity, (d & 1) ? buf_b : buf_a, bound, sizes_dev + d, count_dev, (d & 1) ? buf_a : buf_b, nullptr,
+		                              nullptr, nullptr, nullptr, nullptr, nullptr, sizes_dev + d + 1, scratch, stream);
+		if (rc != RB_OK) return rc;
+		bound *= 12;
 	}
 	return RB_OK;
 }

@@ -143,7 +143,7 @@ class StateHashSet:
 LAST_LAYER_MS = []
 
 
-def bfs_layers(max_depth: int, start=None, is2024: bool | None = None, capacity: int | None = None):
+def bfs_layers(max_depth: int, start=None, is2024: bool | None = None, capacity: int | None = None, chain_items: int = 1 << 18):
 	"""Layer-synchronous BFS closure from `start` (default solved): per-depth counts of newly discovered states
 	(1, 12, 114, 1068, ... for the 20x24 cube) and the StateHashSet.  Everything but one int per layer stays on the device."""
 	is2024 = cube.get_is2024() if is2024 is None else is2024
@@ -155,13 +155,40 @@ def bfs_layers(max_depth: int, start=None, is2024: bool | None = None, capacity:
 	counts = [1]
 	events = [torch.cuda.Event(enable_timing=True) for _ in range(max_depth + 1)]
 	events[0].record()
-	for d in range(max_depth):
+	d = 0
+	if is2024 and chain_items > 0:
+		# the first layers are tiny: they are enqueued back to back with their sizes left on the device (the size of layer d+1 is
+		# the n_new of layer d; grids and buffers are sized for the upper bound 12^d) and all counts are read with one sync
+		n0, layers, bound = frontier.shape[0], 0, frontier.shape[0]
+		while layers < max_depth - 1 and 12 * bound <= chain_items:
+			layers, bound = layers + 1, 12 * bound
+		if layers:
+			sizes = torch.zeros(layers + 1, dtype=torch.int32, device=hs.dev)
+			sizes[0] = n0
+			hs._reserve(2 * bound)
+			bufs = [torch.empty(bound, 20, dtype=torch.int8, device=hs.dev) for _ in range(2)]
+			bufs[0][:n0] = frontier
+			scratch = hs._scratch_for(N.lib.rb_frontier_scratch_bytes(hs.rep, bound // 12))
+			N.check(N.lib.rb_frontier_expand_chain(hs.rep, N.ptr(hs.table), hs.capacity, N.ptr(bufs[0]), N.ptr(bufs[1]), n0, layers, N.ptr(sizes),
+												   N.ptr(hs.count), N.ptr(scratch), N.stream_handle()))
+			hs._upper += 2 * bound
+			frontier, d = bufs[layers & 1], layers
+			for k in range(1, d + 1):
+				events[k].record()
+		if d:
+			got = sizes[1:d + 1].tolist()
+			if min(got) < 0:
+				read_count(sizes[1:d + 1].min())
+			counts += [int(x) for x in got]
+			frontier = frontier[:counts[-1]]
+	while d < max_depth:
 		last = d == max_depth - 1                    # nobody expands the last layer's states: they are entered into the set and counted only
 		out = hs.expand(frontier, parents=False, solved=False, states=not last)
 		events[d + 1].record()
 		n_new = read_count(out["n_new"])
 		frontier = out["next"][:n_new] if out["next"] is not None else None
 		counts.append(n_new)
+		d += 1
 	global LAST_LAYER_MS
 	LAST_LAYER_MS = [events[d].elapsed_time(events[d + 1]) for d in range(max_depth)]      # device time per layer (diagnostics)
 	return counts, hs
