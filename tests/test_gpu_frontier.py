@@ -386,3 +386,18 @@ def test_astar_batch_686_matches_harness_traces(golden, use_graphs):
 	assert one.search(g["astar_full_start"], None, 20000) == bool(g["astar_full_ok"])
 	assert len(one) == int(g["astar_full_len"]) and list(one.action_queue) == g["astar_full_queue"].tolist()
 	assert one.search(O.solved_2024(), None, 100) and len(one) == 0 and not one.action_queue
+
+
+def test_chained_layers_equal_layer_by_layer_expansion():
+	"""`rb_frontier_expand_chain` (layer sizes left on the device, grids sized for the upper bound 12^d) against one
+	`rb_frontier_expand` per layer with a host read in between: same counts, same numbering of every state."""
+	from rl_rubiks_b200 import cube
+	from rl_rubiks_b200.frontier import bfs_layers
+	start = O.scramble(np.array([0, 3, 5]), np.array([1, 0, 1]), True)
+	for depth in (1, 2, 5):
+		c_chain, hs_chain = bfs_layers(depth, start=start, is2024=True)
+		c_plain, hs_plain = bfs_layers(depth, start=start, is2024=True, chain_items=0)
+		assert c_chain == c_plain and len(hs_chain) == len(hs_plain) == sum(c_plain)
+		probe = cube.scramble_batch(np.random.RandomState(depth).randint(0, 12, (3000, depth)).astype(np.uint8), start=np.repeat(start[None], 3000, 0))
+		idx = hs_plain.lookup(probe)
+		assert (idx > 0).all() and (hs_chain.lookup(probe) == idx).all()
