@@ -401,3 +401,19 @@ def test_chained_layers_equal_layer_by_layer_expansion():
 		probe = cube.scramble_batch(np.random.RandomState(depth).randint(0, 12, (3000, depth)).astype(np.uint8), start=np.repeat(start[None], 3000, 0))
 		idx = hs_plain.lookup(probe)
 		assert (idx > 0).all() and (hs_chain.lookup(probe) == idx).all()
+
+
+def test_hash_set_batches_are_deterministic_under_contention():
+	"""Stand-in for racecheck on the hash kernels: a batch with heavy in-batch duplication (every state ~16 times, claimed and raced
+	for by many threads at once) must give the same seen / first / index arrays on every run and equal the dict semantics."""
+	from rl_rubiks_b200.frontier import StateHashSet
+	base = _states(4000, True, seed=1, depth=12)
+	rng = np.random.RandomState(2)
+	batch = base[rng.randint(0, len(base), 64000)]
+	want = O.SeenSet().insert_unique(batch)
+	for _ in range(6):
+		hs = StateHashSet(1 << 18, True)
+		seen, first, idx = hs.insert_unique(batch)
+		assert (seen == want[0]).all() and (first == want[1]).all() and (idx == want[2]).all()
+		seen2, first2, idx2 = hs.insert_unique(batch[::-1].copy())
+		assert seen2.all() and (idx2 == idx[::-1]).all() and len(hs) == int(want[1].sum())
