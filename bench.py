@@ -54,8 +54,10 @@ def ncu_capture():
 			   "dram_pct": m["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"],
 			   "shared_wavefronts": m["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"],
 			   "shared_bank_conflict_replays": m["l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"],
-			   "resource": "integer ALU + heavy-FMA issue at 8 warps per sub-partition (math_pipe_throttle / dispatch stalls); relieving l1tex "
-						   "(94 %) does not speed the kernel up: profiles/r2_scramble_pipe_experiments.txt"}
+			   "mio_throttle_stall_per_issue": m["smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio"],
+			   "resource": "shared-memory wavefronts of the table gathers (l1tex 95 %, MIO throttle the top stall; half are bank-conflict "
+						   "replays), with the integer ALU pipe right behind: conflict-free table reads (throw-away builds) reach 0.72 ms "
+						   "= 0.43 of the roofline, where the ALU pipe takes over: profiles/r2_scramble_pipe_experiments.txt"}
 		return per_cube, lim, "ncu --set full, " + os.path.relpath(NCU_SUMMARY, ROOT)
 	except (OSError, KeyError, IndexError, ValueError) as e:
 		return None, None, f"no ncu summary ({e})"
@@ -412,7 +414,7 @@ def run_gpu(args):
 					 "traffic_source": ncu_src + " (dram read + write of one 2^24-cube launch, scaled by cubes)",
 					 "peak_source": peak_src, "kernel": "rbs::k_scramble_macro3<1, 1>", "kernel_ms": kernel_ms,
 					 "algorithmic_bytes_per_launch": BYTES_PER_CUBE * n,
-					 "note": "100 dependent moves per 120 bytes: the multi-move scramble is instruction-bound (integer ALU + heavy-FMA issue), not HBM-bound: DESIGN.md 3.1",
+					 "note": "100 dependent moves per 120 bytes: the multi-move scramble is bound by the shared-memory table gathers with the integer ALU pipe right behind (measured floor of the design 0.72 ms = 0.43), not HBM-bound: DESIGN.md 3.1",
 					 "limiter": dict(limiter, source=ncu_src) if limiter else None},
 		"cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": cpu_kind, "sample": cpu_sample_text(cpu_kind, cores, cpu_chunks, depth, cpu_dt),
 						 "single_process": {"value": one_value, "cores": 1, "kind": cpu_kind, "sample": cpu_sample_text(cpu_kind, 1, 4, depth, one_dt)},
