@@ -41,6 +41,8 @@ static int rb_fail(int code, const char* fmt, const char* a = "", const char* b 
 
 static inline int rb_grid(int64_t work_items, int per_block, int blocks_per_sm) {
 	int64_t need = (work_items + per_block - 1) / per_block;
+	static const int exp_blocks = getenv("RB_GRID_BLOCKS") ? atoi(getenv("RB_GRID_BLOCKS")) : 0;       // EXPERIMENT
+	if (exp_blocks > 0) blocks_per_sm = exp_blocks;
 	int64_t cap = (int64_t)RB_NUM_SMS * blocks_per_sm;
 	if (need < 1) need = 1;
 	return (int)(need < cap ? need : cap);
