@@ -39,10 +39,14 @@ static int rb_fail(int code, const char* fmt, const char* a = "", const char* b 
 #define RB_REQUIRE(cond, msg)                                                                 \
 	do { if (!(cond)) return rb_fail(RB_ERR_BAD_ARG, "%s (%s)", msg, #cond); } while (0)
 
+// Grid for a grid-stride kernel: enough blocks for the work, at most `blocks_per_sm` per SM.  The caps are measured per kernel
+// (profiles/r2g_grid_sweep.txt): the kernels that mostly WRITE (one-hot rows, 12-neighbour expansion, the ADI batch) are 6-18 %
+// faster with one block per unit of work (kGridUncapped: the block scheduler hands out work as SMs free up, and the address streams
+// of the resident warps are not locked into one fixed stride) than as a persistent grid of 8 blocks per SM; the read + write
+// streaming kernels (multi_rotate) want exactly their resident block count (5 per SM at 46-47 registers: no second, partial wave).
+constexpr int kGridUncapped = 1 << 20;
 static inline int rb_grid(int64_t work_items, int per_block, int blocks_per_sm) {
 	int64_t need = (work_items + per_block - 1) / per_block;
-	static const int exp_blocks = getenv("RB_GRID_BLOCKS") ? atoi(getenv("RB_GRID_BLOCKS")) : 0;       // EXPERIMENT
-	if (exp_blocks > 0) blocks_per_sm = exp_blocks;
 	int64_t cap = (int64_t)RB_NUM_SMS * blocks_per_sm;
 	if (need < 1) need = 1;
 	return (int)(need < cap ? need : cap);

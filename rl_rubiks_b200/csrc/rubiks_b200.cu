@@ -81,13 +81,13 @@ int rb_multi_rotate(int rep, const int8_t* states, const uint8_t* faces, const u
 	RB_INIT();
 	if (rep == RB_REP_2024) {
 		if (aligned(states, 4) && aligned(out, 4))
-			rb2024::k_multi_rotate<<<rb_grid(n, 256, 8), rb2024::kThreads, 0, S(stream)>>>(states, faces, dirs, out, n);
+			rb2024::k_multi_rotate<<<rb_grid(n, 256, 5), rb2024::kThreads, 0, S(stream)>>>(states, faces, dirs, out, n);
 		else
 			rb2024::k_multi_rotate_any<<<rb_grid(n, rb2024::kTile, 2), rb2024::kThreads, 0, S(stream)>>>(states, faces, dirs, out, n);
 		RB_LAUNCHED("multi_rotate_2024");
 	} else {
 		RB_REQUIRE(aligned(states, 4) && aligned(out, 4), "6x8x6 states must be 4-byte aligned");
-		rb686::k_multi_rotate<<<rb_grid(n, rb686::kMrStates * rb686::kWarps, 8), rb686::kThreads, 0, S(stream)>>>(states, faces, dirs, out, n);
+		rb686::k_multi_rotate<<<rb_grid(n, rb686::kMrStates * rb686::kWarps, 5), rb686::kThreads, 0, S(stream)>>>(states, faces, dirs, out, n);
 		RB_LAUNCHED("multi_rotate_686");
 	}
 	return RB_OK;
@@ -124,13 +124,13 @@ static int as_oh_impl(int rep, const int8_t* states, OH* oh, int64_t n, rb_strea
 	const int64_t esz = sizeof(OH);
 	if (rep == RB_REP_2024) {
 		if (aligned(states, 4))
-			rb2024::k_as_oh<OH><<<rb_grid(n, rb2024::kThreads, 6), rb2024::kThreads, 0, S(stream)>>>(states, oh, n, rb_store_policy(n * 480 * esz));
+			rb2024::k_as_oh<OH><<<rb_grid(n, rb2024::kThreads, kGridUncapped), rb2024::kThreads, 0, S(stream)>>>(states, oh, n, rb_store_policy(n * 480 * esz));
 		else
-			rb2024::k_as_oh_any<OH><<<rb_grid(n, 8, 8), rb2024::kThreads, 0, S(stream)>>>(states, oh, n, rb_store_policy(n * 480 * esz));
+			rb2024::k_as_oh_any<OH><<<rb_grid(n, 8, kGridUncapped), rb2024::kThreads, 0, S(stream)>>>(states, oh, n, rb_store_policy(n * 480 * esz));
 		RB_LAUNCHED("as_oh_2024");
 	} else {
 		RB_REQUIRE(aligned(states, 4), "6x8x6 states must be 4-byte aligned");
-		rb686::k_as_oh<OH><<<rb_grid(n * 72, rb686::kThreads * 8, 8), rb686::kThreads, 0, S(stream)>>>(states, oh, n * 72, rb_store_policy(n * 288 * esz));
+		rb686::k_as_oh<OH><<<rb_grid(n * 72, rb686::kThreads * 8, kGridUncapped), rb686::kThreads, 0, S(stream)>>>(states, oh, n * 72, rb_store_policy(n * 288 * esz));
 		RB_LAUNCHED("as_oh_686");
 	}
 	return RB_OK;
@@ -161,17 +161,17 @@ static int expand12_impl(int rep, const int8_t* states, int8_t* children, OH* ch
 	RB_INIT();
 	if (rep == RB_REP_2024) {
 		if (!children_oh && aligned(states, 4) && aligned(children, 16) && aligned(solved, 4))
-			rb2024::k_expand12_states<<<rb_grid(n, rb2024::kExpThreads, 5), rb2024::kExpThreads, 0, S(stream)>>>(states, children, solved, n, rb_store_policy(n * 240));
+			rb2024::k_expand12_states<<<rb_grid(n, rb2024::kExpThreads, kGridUncapped), rb2024::kExpThreads, 0, S(stream)>>>(states, children, solved, n, rb_store_policy(n * 240));
 		else
-			rb2024::k_expand12<OH><<<rb_grid(n, 8, 8), rb2024::kThreads, 0, S(stream)>>>(states, children, children_oh, solved, n,
+			rb2024::k_expand12<OH><<<rb_grid(n, 8, kGridUncapped), rb2024::kThreads, 0, S(stream)>>>(states, children, children_oh, solved, n,
 			                                                                                 rb_store_policy(children_oh ? n * 12 * 480 * esz : n * 240));
 		RB_LAUNCHED("expand12_2024");
 	} else {
 		RB_REQUIRE(aligned(states, 16) && aligned(children, 16), "6x8x6 states must be 16-byte aligned");
 		if (!children_oh && !solved)
-			rb686::k_expand12_states<<<rb_grid(n, rb686::kWarps, 8), rb686::kThreads, 0, S(stream)>>>(states, children, n);
+			rb686::k_expand12_states<<<rb_grid(n, rb686::kWarps, 32), rb686::kThreads, 0, S(stream)>>>(states, children, n);
 		else
-			rb686::k_expand12<OH><<<rb_grid(n, rb686::kWarps, 6), rb686::kThreads, 0, S(stream)>>>(states, children, children_oh, solved, n,
+			rb686::k_expand12<OH><<<rb_grid(n, rb686::kWarps, kGridUncapped), rb686::kThreads, 0, S(stream)>>>(states, children, children_oh, solved, n,
 			                                                                                     rb_store_policy(n * 12 * (children_oh ? 288 * (esz + 1) : 288)));
 		RB_LAUNCHED("expand12_686");
 	}
@@ -268,11 +268,11 @@ static int launch_sequence(int rep, bool with_children, const uint8_t* faces, co
 	const int pol = rb_store_policy(rows * (rep == RB_REP_2024 ? ((oh || children_oh) ? 480 * esz : 20) : ((oh || children_oh) ? 288 * (esz + 1) : 288)));
 	if (rep == RB_REP_2024 && !with_children && !oh && aligned(states, 4)) {
 		// states / flags only: thread per game, register LUT, staged coalesced output
-		rb2024::k_sequence_states<<<rb_grid(games, rb2024::kThreads, 4), rb2024::kThreads, 0, S(stream)>>>(faces, dirs, games, depth, ws,
+		rb2024::k_sequence_states<<<rb_grid(games, rb2024::kThreads, 24), rb2024::kThreads, 0, S(stream)>>>(faces, dirs, games, depth, ws,
 		                                                                                             states, solved_states);
 		RB_LAUNCHED("sequence_states_2024");
 	} else if (rep == RB_REP_2024) {
-		const int grid = rb_grid(units, 8, 8);
+		const int grid = rb_grid(units, 8, kGridUncapped);
 		if (with_children)
 			rb2024::k_sequence<true, OH><<<grid, rb2024::kThreads, 0, S(stream)>>>(faces, dirs, games, depth, ws, chunk, states, oh,
 			                                                                   solved_states, children, children_oh, solved_children, pol);
