@@ -378,7 +378,7 @@ static bool pow2(int64_t x) { return x > 0 && (x & (x - 1)) == 0; }
 
 int rb_hashset_clear(void* table, int64_t capacity, rb_stream_t stream) {
 	RB_REQUIRE_TABLE(table, capacity);
-	rbf::k_clear<<<rb_grid(2 * capacity, rbf::kThreads * 4, 8), rbf::kThreads, 0, S(stream)>>>(table, capacity);
+	rbf::k_clear<<<rb_grid(2 * capacity, rbf::kThreads * 4, kGridUncapped), rbf::kThreads, 0, S(stream)>>>(table, capacity);
 	RB_LAUNCHED("hashset_clear");
 	return RB_OK;
 }
