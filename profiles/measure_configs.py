@@ -194,6 +194,28 @@ def main():
 		report("expand12_686 states only (C3)", n * 3744, 12 * n, "children",
 			   lambda: N.check(N.lib.rb_expand12(N.REP_686, N.ptr(s), N.ptr(ch), None, None, n, sh)), n=n)
 		del ch, fl
+		n4 = (1 << 17) // q
+		s4 = s[:n4].contiguous()
+		ch4 = torch.empty(12 * n4, 6, 8, 6, dtype=torch.int8, device=dev)
+		oh4 = torch.empty(12 * n4, 288, dtype=torch.float32, device=dev)
+		fl4 = torch.empty(12 * n4, dtype=torch.uint8, device=dev)
+		report("expand12_686 states+oh+solved", n4 * (288 + 12 * (288 + 1152 + 1)), 12 * n4, "children",
+			   lambda: N.check(N.lib.rb_expand12(N.REP_686, N.ptr(s4), N.ptr(ch4), N.ptr(oh4), N.ptr(fl4), n4, sh)), n=n4)
+		del s4, ch4, oh4, fl4
+		games, gd = 1000, 25
+		ga = torch.randint(0, 12, (gd, games), dtype=torch.uint8, device=dev, generator=g)
+		nst = games * gd
+		st = torch.empty(nst, 6, 8, 6, dtype=torch.int8, device=dev)
+		oh = torch.empty(nst, 288, dtype=torch.float32, device=dev)
+		ss = torch.empty(nst, dtype=torch.uint8, device=dev)
+		ch = torch.empty(12 * nst, 6, 8, 6, dtype=torch.int8, device=dev)
+		coh = torch.empty(12 * nst, 288, dtype=torch.float32, device=dev)
+		sc = torch.empty(12 * nst, dtype=torch.uint8, device=dev)
+		report("sequence_686 states+oh (1000 x 25)", nst * (1 + 288 + 1152), nst, "states",
+			   lambda: N.check(N.lib.rb_sequence_scramble(N.REP_686, N.ptr(ga), None, games, gd, 1, N.ptr(st), N.ptr(oh), None, sh)), n=nst)
+		report("adi_generate_686 (1000 x 25)", nst * (1 + 288 + 1152 + 1 + 12 * (288 + 1152 + 1)), nst, "samples",
+			   lambda: N.check(N.lib.rb_adi_generate(N.REP_686, N.ptr(ga), None, games, gd, 1, N.ptr(st), N.ptr(oh), N.ptr(ch), N.ptr(coh), N.ptr(ss), N.ptr(sc), sh)), n=nst)
+		del ga, st, oh, ss, ch, coh, sc
 		n3, depth = (1 << 20) // q, 100
 		acts = torch.randint(0, 12, (n3, depth), dtype=torch.uint8, device=dev, generator=g)
 		o3 = torch.empty(n3, 6, 8, 6, dtype=torch.int8, device=dev)
