@@ -110,28 +110,38 @@ k_multi_rotate(const int8_t* __restrict__ in, const uint8_t* __restrict__ faces,
 	__syncthreads();
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	uint32_t* tile = s_tile[wib];
-	const int64_t n_chunks = (n + 31) / 32, stride = (int64_t)gridDim.x * kWarpsPerBlock;
+	const int64_t n_chunks = (n + 31) / 32, n_full = n / 32, stride = (int64_t)gridDim.x * kWarpsPerBlock;
 	uint32_t nxt[5], nf = 0, nd = 0;
+	// Only the last chunk can be ragged: whole chunks (warp-uniform test) run without the per-word bounds predicates, which were a
+	// quarter of the ALU-pipe instructions of this ALU-bound kernel.
 	auto fetch = [&](int64_t c) {                              // chunk c -> registers (words lane, lane+32, ...; action bytes)
 		const int64_t base = c * 32;
-		const int cnt = (int)min((int64_t)32, n - base);
 		const uint32_t* src = reinterpret_cast<const uint32_t*>(in + base * 20);
+		if (c < n_full) {
 #pragma unroll
-		for (int k = 0; k < 5; ++k) nxt[k] = lane + 32 * k < cnt * 5 ? __ldcs(src + lane + 32 * k) : 0u;
-		nf = lane < cnt ? faces[base + lane] : 0u;
-		nd = (dirs && lane < cnt) ? dirs[base + lane] : 0u;
+			for (int k = 0; k < 5; ++k) nxt[k] = __ldcs(src + lane + 32 * k);
+			nf = faces[base + lane];
+			nd = dirs ? dirs[base + lane] : 0u;
+		} else {
+			const int cnt = (int)(n - base);
+#pragma unroll
+			for (int k = 0; k < 5; ++k) nxt[k] = lane + 32 * k < cnt * 5 ? __ldcs(src + lane + 32 * k) : 0u;
+			nf = lane < cnt ? faces[base + lane] : 0u;
+			nd = (dirs && lane < cnt) ? dirs[base + lane] : 0u;
+		}
 	};
 	int64_t c = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
 	if (c < n_chunks) fetch(c);
 	for (; c < n_chunks; c += stride) {
 		const int64_t base = c * 32;
-		const int cnt = (int)min((int64_t)32, n - base);
+		const bool full = c < n_full;
+		const int cnt = full ? 32 : (int)(n - base);
 		const uint32_t a = dirs ? rb_action_of(nf, nd) : rb_clamp_action(nf);
 #pragma unroll
 		for (int k = 0; k < 5; ++k) tile[lane + 32 * k] = nxt[k];
 		if (c + stride < n_chunks) fetch(c + stride);
 		__syncwarp();
-		if (lane < cnt) {
+		if (full || lane < cnt) {
 			uint32_t w[5], rc[6], re[6];
 #pragma unroll
 			for (int k = 0; k < 5; ++k) w[k] = tile[lane * 5 + k];
@@ -140,7 +150,15 @@ k_multi_rotate(const int8_t* __restrict__ in, const uint8_t* __restrict__ faces,
 #pragma unroll
 			for (int k = 0; k < 5; ++k) tile[lane * 5 + k] = w[k];
 		}
-		warp_store_states(reinterpret_cast<uint32_t*>(out + base * 20), tile, cnt * 5, lane);
+		uint32_t* dst = reinterpret_cast<uint32_t*>(out + base * 20);
+		if (full) {
+			__syncwarp();
+#pragma unroll
+			for (int k = 0; k < 5; ++k) __stcs(dst + lane + 32 * k, tile[lane + 32 * k]);
+			__syncwarp();
+		} else {
+			warp_store_states(dst, tile, cnt * 5, lane);
+		}
 	}
 }
 
