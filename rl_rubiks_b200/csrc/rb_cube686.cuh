@@ -244,6 +244,13 @@ k_expand12_states(const int8_t* __restrict__ in, int8_t* __restrict__ children, 
 	__syncthreads();
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	uint32_t* buf = s_buf[wib];
+	// Word i = lane + 32 r of the 864 output words is word i % 72 of action i / 72, i.e. table entry i: the same 27 entries for
+	// every parent this lane works on.  They are read once into registers (two per register); the kernel was bound by its
+	// shared-memory wavefronts (l1tex 97 %), a fifth of which were these table reads.
+	uint32_t pairs[14];
+#pragma unroll
+	for (int r = 0; r < 14; ++r) pairs[r] = (uint32_t)s_tab[lane + 64 * r] | (r < 13 ? (uint32_t)s_tab[lane + 64 * r + 32] << 16 : 0u);
+	const uint16_t* src16 = reinterpret_cast<const uint16_t*>(buf);
 	for (int64_t p = (int64_t)blockIdx.x * kWarps + wib; p < n; p += (int64_t)gridDim.x * kWarps) {
 		const uint32_t* src = reinterpret_cast<const uint32_t*>(in) + p * 72;
 		uint32_t* dst = reinterpret_cast<uint32_t*>(children) + p * 864;
@@ -251,10 +258,10 @@ k_expand12_states(const int8_t* __restrict__ in, int8_t* __restrict__ children, 
 		buf[lane + 32] = __ldcs(src + lane + 32);
 		if (lane < 8) buf[lane + 64] = __ldcs(src + lane + 64);
 		__syncwarp();
-#pragma unroll 9
+#pragma unroll
 		for (int r = 0; r < 27; ++r) {
-			const uint32_t i = lane + 32 * r, a = (i * 911u) >> 16;   // i / 72 for i < 864
-			__stcs(dst + i, gather_word(s_tab, reinterpret_cast<const uint16_t*>(buf), a, i - 72u * a));
+			const uint32_t pair = (r & 1) ? pairs[r >> 1] >> 16 : pairs[r >> 1] & 0xffffu;
+			__stcs(dst + lane + 32 * r, (uint32_t)src16[pair & 0xffu] | ((uint32_t)src16[pair >> 8] << 16));
 		}
 		__syncwarp();
 	}
