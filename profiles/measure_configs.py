@@ -151,6 +151,10 @@ def main():
 		oh = torch.empty(n, 480, dtype=torch.float32, device=dev)
 		report("sequence_2024 states+oh (7500 x 30)", n * (1 + 20 + 1920), n, "states",
 			   lambda: N.check(N.lib.rb_sequence_scramble(N.REP_2024, N.ptr(a), None, games, depth, 1, N.ptr(st), N.ptr(oh), None, sh)), n=n)
+		gs, ds = 1000, 25
+		a_s = torch.randint(0, 12, (ds, gs), dtype=torch.uint8, device=dev, generator=g)
+		report("sequence_2024 states+oh (1000 x 25)", gs * ds * (1 + 20 + 1920), gs * ds, "states",
+			   lambda: N.check(N.lib.rb_sequence_scramble(N.REP_2024, N.ptr(a_s), None, gs, ds, 1, N.ptr(st), N.ptr(oh), None, sh)), n=gs * ds)
 		games2, depth2 = (1 << 20) // q, 100
 		a2 = torch.randint(0, 12, (depth2, games2), dtype=torch.uint8, device=dev, generator=g)
 		st2 = torch.empty(games2 * depth2, 20, dtype=torch.int8, device=dev)

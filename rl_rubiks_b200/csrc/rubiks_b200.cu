@@ -237,17 +237,22 @@ int rb_scramble(int rep, const uint8_t* actions, int64_t stride_cube, int64_t st
 	return RB_OK;
 }
 
-static int sequence_chunk(int64_t games, int depth, bool fine) {
-	// (game, chunk of positions) units per SM: enough for ~8 warps x 8 blocks per SM without replaying more than needed -- a unit
-	// replays its game's prefix to reach its chunk.  `fine` (the 20x24 ADI generator: 13 one-hot rows = 25 kB of stores per position
-	// against at most `depth` byte lookups per lane of replay): one position per unit balances the single wave of a rollout-sized
-	// batch (1000 x 25: 0.117 -> 0.111 ms; 7500 x 30 with bf16 rows 0.498 -> 0.461 ms).  RB_SEQ_UNITS_PER_SM overrides the fine value.
-	static const int fine_per_sm = [] { const char* e = getenv("RB_SEQ_UNITS_PER_SM"); const int v = e ? atoi(e) : 1024; return v > 0 ? v : 1024; }();
-	int64_t target_units = (int64_t)RB_NUM_SMS * (fine ? fine_per_sm : 64);
+static int sequence_chunk(int64_t games, int depth, int units_per_sm) {
+	// (game, chunk of positions) units per SM -- a unit replays its game's prefix to reach its chunk, so finer units balance the
+	// grid better but replay more.  Measured (profiles/r2g_grid_sweep.txt): the 20x24 ADI generator (13 one-hot rows = 25 kB of
+	// stores per position against at most `depth` byte lookups per lane of replay) wants one position per unit (1024 per SM;
+	// 1000 x 25: 0.117 -> 0.111 ms, 7500 x 30 with bf16 rows 0.498 -> 0.461 ms); the 20x24 sequence with one one-hot row per position
+	// 256 per SM (7500 x 30: 0.084 -> 0.074 ms; 1024 per SM: 0.096 ms); everything else 64.  RB_SEQ_UNITS_PER_SM overrides the ADI value.
+	int64_t target_units = (int64_t)RB_NUM_SMS * units_per_sm;
 	int64_t chunks_per_game = (target_units + games - 1) / games;
 	if (chunks_per_game < 1) chunks_per_game = 1;
 	if (chunks_per_game > depth) chunks_per_game = depth;
 	return (int)((depth + chunks_per_game - 1) / chunks_per_game);
+}
+static int sequence_units_per_sm(int rep, bool with_children, bool with_oh) {
+	static const int adi_per_sm = [] { const char* e = getenv("RB_SEQ_UNITS_PER_SM"); const int v = e ? atoi(e) : 1024; return v > 0 ? v : 1024; }();
+	if (rep != RB_REP_2024) return 64;
+	return with_children ? adi_per_sm : (with_oh ? 256 : 64);
 }
 
 extern "C++" {
@@ -262,7 +267,7 @@ static int launch_sequence(int rep, bool with_children, const uint8_t* faces, co
 	RB_REQUIRE(aligned(oh, 16) && aligned(children_oh, 16), "one-hot outputs must be 16-byte aligned");
 	RB_INIT();
 	const int ws = with_solved ? 1 : 0;
-	const int chunk = sequence_chunk(games, depth, with_children && rep == RB_REP_2024);
+	const int chunk = sequence_chunk(games, depth, sequence_units_per_sm(rep, with_children, oh != nullptr));
 	const int64_t units = (int64_t)games * ((depth + chunk - 1) / chunk);
 	const int64_t rows = (int64_t)games * depth * (with_children ? 13 : 1);
 	const int pol = rb_store_policy(rows * (rep == RB_REP_2024 ? ((oh || children_oh) ? 480 * esz : 20) : ((oh || children_oh) ? 288 * (esz + 1) : 288)));
