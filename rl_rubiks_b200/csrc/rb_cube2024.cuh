@@ -21,9 +21,11 @@ constexpr int kOhVec = kOhWidth / 4;    // 120 float4 per one-hot row
 // Register LUT.  One move on a cubie-major state is 20 lookups new[j] = lut[a][kind(j)][s[j]] in a 24-entry byte
 // table.  Done through shared memory that is 20 data-dependent LDS.U8 per state with random bank conflicts (the first
 // version of these kernels: 25 % of the HBM roofline).  Here the two 24-byte rows of the state's action sit in 12
-// registers and PRMT is the lookup: for a word of 4 cubie values, selector nibbles (s & 7) pick the candidates from
-// entries 0-7, 8-15 and 16-23, and byte masks made from bit 3 / bit 4 of s (PRMT sign-replicate mode) choose among
-// them: 11 ALU-pipe instructions per 4 lookups, no memory access.
+// registers and PRMT is the lookup.  For a word of 4 cubie values the selector nibbles are s & 15: bit 3 of a PRMT selector
+// nibble means "replicate the sign of the selected byte", and every table entry is < 24, so a lookup in entries 0-7 / 16-23
+// (selector s & 15) returns 0x00 exactly for the values 8-15, and a lookup in entries 8-15 with the selector's bit 3 flipped
+// returns 0x00 for everything but the values 8-15 -- the sign mode does the range masking.  Only the choice between entries
+// 0-7 and 16-23 (bit 4 of s) needs a byte mask: 10 ALU-pipe instructions per 4 lookups, no memory access.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t prmt_r(uint32_t a, uint32_t b, uint32_t sel) {
 	uint32_t r;
@@ -32,21 +34,20 @@ __device__ __forceinline__ uint32_t prmt_r(uint32_t a, uint32_t b, uint32_t sel)
 }
 
 struct LutSel {              // per state word, independent of the action: reusable for all 12 actions in expand12
-	uint32_t sel, m1, m2;
+	uint32_t sel, selx, m2;
 };
 __device__ __forceinline__ LutSel lut_sel(uint32_t w) {
 	LutSel q;
-	const uint32_t t = w & 0x07070707u;
-	const uint32_t y = t | (t >> 4);                           // byte 0 = s0&7 | (s1&7)<<4, byte 2 = s2&7 | (s3&7)<<4
-	q.sel = prmt_r(y, y, 0x3320u);                             // low 16 bits = the four selector nibbles
-	q.m1 = prmt_r(w * 16u, 0u, 0xba98u);                       // 0xff where bit 3 of s is set (entries 8-15)
+	const uint32_t y = (w & 0x0f0f0f0fu) | ((w >> 4) & 0xf0f0f0f0u);  // byte 0 = s0&15 | (s1&15)<<4, byte 2 = s2&15 | (s3&15)<<4
+	q.sel = prmt_r(y, y, 0x3320u);                             // low 16 bits = the four selector nibbles (PRMT reads no more)
+	q.selx = q.sel ^ 0x8888u;                                  // bit 3 of every nibble flipped: live for the values 8-15 only
 	q.m2 = prmt_r(w * 8u, 0u, 0xba98u);                        // 0xff where bit 4 of s is set (entries 16-23)
 	return q;
 }
 // row: the 24-byte table as 6 words (entries 4k..4k+3 in word k)
 __device__ __forceinline__ uint32_t lut24(const uint32_t* __restrict__ row, const LutSel& q) {
-	const uint32_t c0 = prmt_r(row[0], row[1], q.sel), c1 = prmt_r(row[2], row[3], q.sel), c2 = prmt_r(row[4], row[5], q.sel);
-	const uint32_t r = (c1 & q.m1) | (c0 & ~q.m1);
+	const uint32_t c0 = prmt_r(row[0], row[1], q.sel), c1 = prmt_r(row[2], row[3], q.selx), c2 = prmt_r(row[4], row[5], q.sel);
+	const uint32_t r = c0 | c1;                                // s < 16: the entry (the other lookup gave 0); s >= 16: c0 is stale
 	return (c2 & q.m2) | (r & ~q.m2);
 }
 // Row fetch.  Lanes of a warp hold different actions, and the 64-byte row pairs of the plain LUT all start in bank

@@ -325,3 +325,39 @@ def _render_solved(ch, cd, eh, ed, s2024):
 		for k in range(2):
 			out[rows, ed[e, s2024[:, 8 + e], k]] = eye[eh[e, k] // 8]
 	return out
+
+
+def _prmt_word(a: int, b: int, sel: int) -> int:
+	"""prmt.b32 in its default mode on scalar words: nibble k of `sel` (low 16 bits) picks byte (nibble & 7) of {a, b}; bit 3 of
+	the nibble replicates that byte's sign bit instead."""
+	src = [(a >> (8 * i)) & 0xff for i in range(4)] + [(b >> (8 * i)) & 0xff for i in range(4)]
+	out = 0
+	for k in range(4):
+		nib = (sel >> (4 * k)) & 0xf
+		byte = src[nib & 7]
+		if nib & 8:
+			byte = 0xff if byte & 0x80 else 0x00
+		out |= byte << (8 * k)
+	return out
+
+
+def test_register_lut_formulation_equals_the_table():
+	"""rb_cube2024.cuh lut_sel / lut24: selector nibbles s & 15 with PRMT's sign-replicate bit doing the range masking, one byte mask
+	for bit 4.  Emulated on scalar words for every action row, both kinds, and every 4-tuple pattern of values 0..23."""
+	from oracle import cube_oracle as O
+	lut = O.build_lut2024()                                     # (12, 2, 24): new value of a cubie with value s under action a
+	rng = np.random.RandomState(0)
+	words = [tuple(rng.randint(0, 24, 4)) for _ in range(400)] + [(s, s, s, s) for s in range(24)] + [(0, 7, 8, 15), (16, 23, 15, 8), (23, 0, 16, 7)]
+	for a in range(12):
+		for kind in range(2):
+			row = [int.from_bytes(bytes(int(x) for x in lut[a, kind, 4 * k:4 * k + 4]), "little") for k in range(6)]
+			for vals in words:
+				w = int.from_bytes(bytes(int(v) for v in vals), "little")
+				y = (w & 0x0f0f0f0f) | ((w >> 4) & 0xf0f0f0f0)
+				sel = _prmt_word(y, y, 0x3320)
+				selx = sel ^ 0x8888
+				m2 = _prmt_word((w * 8) & 0xffffffff, 0, 0xba98)
+				c0, c1, c2 = _prmt_word(row[0], row[1], sel), _prmt_word(row[2], row[3], selx), _prmt_word(row[4], row[5], sel)
+				got = (c2 & m2) | ((c0 | c1) & ~m2 & 0xffffffff)
+				want = int.from_bytes(bytes(int(lut[a, kind, v]) for v in vals), "little")
+				assert got == want, (a, kind, vals)
