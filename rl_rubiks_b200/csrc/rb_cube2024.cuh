@@ -562,7 +562,7 @@ k_sequence(const uint8_t* __restrict__ faces, const uint8_t* __restrict__ dirs, 
 constexpr int kSeqGroup = 8;                    // positions staged per flush
 constexpr int kSeqPitch = kSeqGroup * 5 + 1;    // words per game in the staging tile
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 k_sequence_states(const uint8_t* __restrict__ faces, const uint8_t* __restrict__ dirs, int games, int depth, int with_solved,
                   int8_t* __restrict__ states, uint8_t* __restrict__ solved_states) {
 	__shared__ uint4 s_rows[kRowsX8Vec];
@@ -575,21 +575,44 @@ k_sequence_states(const uint8_t* __restrict__ faces, const uint8_t* __restrict__
 	const uint32_t v0 = sv[0], v1 = sv[1], v2 = sv[2], v3 = sv[3], v4 = sv[4];
 	const int n_warps_games = (games + 31) / 32;
 	const int moves = depth - with_solved;                     // action rows used: 0 .. moves-1
+	const int64_t game_pitch = (int64_t)depth * 5;
+	// Flush of a full group from a full warp of games: 1280 words, word i = lane + 32 j belongs to game i / 40, offset i % 40.
+	// Five steps advance i by 160 = 4 games exactly, so (game, offset) of steps u = 0..4 are per-lane constants and step
+	// j = 5 t + u is game 4 t + (that game): no division and no index arithmetic beyond one multiply-add per word in the loop (the
+	// general form below cost ~10 instructions per word, a quarter of the kernel's instruction count).
+	int64_t goff[5];
+	int soff[5];
+#pragma unroll
+	for (int u = 0; u < 5; ++u) {
+		const int i = lane + 32 * u, fg = i / (kSeqGroup * 5), fk = i - fg * (kSeqGroup * 5);
+		goff[u] = fg * game_pitch + fk;
+		soff[u] = fg * kSeqPitch + fk;
+	}
 	for (int wg = blockIdx.x * kWarpsPerBlock + wib; wg < n_warps_games; wg += gridDim.x * kWarpsPerBlock) {
 		const int g0 = wg * 32, g = g0 + lane, cnt = min(32, games - g0);
 		const bool live = lane < cnt;
 		uint32_t w[5] = {v0, v1, v2, v3, v4};
 		uint32_t act[kSeqGroup];
+		const uint8_t* fcol = faces + g;                        // this lane's game: element m is fcol[m * games]
+		const uint8_t* dcol = dirs ? dirs + g : nullptr;
 		auto fetch = [&](int m0) {                             // actions of moves m0 .. m0+7 of this lane's game (coalesced over lanes)
+			if (live && m0 >= 0 && m0 + kSeqGroup <= moves) {      // whole group inside the sequence: no per-move bounds
 #pragma unroll
-			for (int k = 0; k < kSeqGroup; ++k) {
-				const int m = m0 + k;
-				uint32_t a = 12u;
-				if (live && m >= 0 && m < moves) {
-					const int64_t idx = (int64_t)m * games + g;
-					a = dirs ? rb_action_of(faces[idx], dirs[idx]) : rb_clamp_action(faces[idx]);
+				for (int k = 0; k < kSeqGroup; ++k) {
+					const int64_t off = (int64_t)(m0 + k) * games;
+					act[k] = dcol ? rb_action_of(fcol[off], dcol[off]) : rb_clamp_action(fcol[off]);
 				}
-				act[k] = a;
+			} else {
+#pragma unroll
+				for (int k = 0; k < kSeqGroup; ++k) {
+					const int m = m0 + k;
+					uint32_t a = 12u;
+					if (live && m >= 0 && m < moves) {
+						const int64_t off = (int64_t)m * games;
+						a = dcol ? rb_action_of(fcol[off], dcol[off]) : rb_clamp_action(fcol[off]);
+					}
+					act[k] = a;
+				}
 			}
 		};
 		// position d holds the state after d + 1 - with_solved moves: with_solved shifts the moves by one position
@@ -600,10 +623,10 @@ k_sequence_states(const uint8_t* __restrict__ faces, const uint8_t* __restrict__
 			for (int k = 0; k < kSeqGroup; ++k) cur[k] = act[k];
 			if (d0 + kSeqGroup < depth) fetch(d0 + kSeqGroup - with_solved);
 			uint32_t flags_lo = 0, flags_hi = 0;
+			const int npos = min(kSeqGroup, depth - d0);
 #pragma unroll
 			for (int k = 0; k < kSeqGroup; ++k) {
-				const int d = d0 + k;
-				if (d < depth) {
+				if (k < npos) {
 					if (cur[k] < 12u) {                        // 12 = no move (the leading solved position / padding)
 						uint32_t rc[6], re[6];
 						load_rows(s_rows, cur[k], lane, rc, re);
@@ -611,22 +634,25 @@ k_sequence_states(const uint8_t* __restrict__ faces, const uint8_t* __restrict__
 					}
 #pragma unroll
 					for (int q = 0; q < 5; ++q) stage[lane * kSeqPitch + k * 5 + q] = w[q];
-					const uint32_t ok = (w[0] == v0) & (w[1] == v1) & (w[2] == v2) & (w[3] == v3) & (w[4] == v4);
-					if (k < 4) flags_lo |= ok << (8 * k); else flags_hi |= ok << (8 * (k - 4));
+					if (solved_states) {
+						const uint32_t ok = (w[0] == v0) & (w[1] == v1) & (w[2] == v2) & (w[3] == v3) & (w[4] == v4);
+						if (k < 4) flags_lo |= ok << (8 * k); else flags_hi |= ok << (8 * (k - 4));
+					}
 				}
 			}
 			__syncwarp();
-			const int npos = min(kSeqGroup, depth - d0), per_game = npos * 5;
 			if (states) {
 				uint32_t* out_w = reinterpret_cast<uint32_t*>(states) + ((int64_t)g0 * depth + d0) * 5;
-				const int64_t game_pitch = (int64_t)depth * 5;
-				if (npos == kSeqGroup) {                           // full group: 40 words per game, constant division
-#pragma unroll 4
-					for (int i = lane; i < cnt * (kSeqGroup * 5); i += 32) {
-						const int gi = (i * 1639) >> 16, k = i - gi * (kSeqGroup * 5);      // i / 40 for i < 1280
-						__stcs(out_w + gi * game_pitch + k, stage[gi * kSeqPitch + k]);
+				if (npos == kSeqGroup && cnt == 32) {              // full group, full warp of games: the hoisted indices
+#pragma unroll 2
+					for (int t8 = 0; t8 < 8; ++t8) {
+						uint32_t* o = out_w + (int64_t)(4 * t8) * game_pitch;
+						const uint32_t* s = stage + 4 * t8 * kSeqPitch;
+#pragma unroll
+						for (int u = 0; u < 5; ++u) __stcs(o + goff[u], s[soff[u]]);
 					}
 				} else {
+					const int per_game = npos * 5;
 					for (int i = lane; i < cnt * per_game; i += 32) {
 						const int gi = i / per_game, k = i - gi * per_game;
 						out_w[gi * game_pitch + k] = stage[gi * kSeqPitch + k];
