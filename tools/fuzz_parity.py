@@ -53,7 +53,9 @@ def case_scramble():
 	is2024 = rng.rand() < 0.7
 	cube.set_is2024(bool(is2024))
 	n = min(rand_n(), 6000 if is2024 else 600)
-	depth = int(rng.choice([0, 1, 2, 3, 19, 20, 21, 23, 24, 25, 47, 48, 64, 96, 100, 128, 256, rng.randint(1, 420)]))
+	depth = int(rng.choice([0, 1, 2, 3, 19, 20, 21, 23, 24, 25, 47, 48, 64, 96, 100, 128, 256, rng.randint(1, 420), rng.randint(400, 1000)]))
+	if depth > 420:
+		n = min(n, 700)
 	acts = rng.randint(0, 12, (n, depth)).astype(np.uint8)
 	f, d = O.indices_to_actions(acts)
 	start = rand_states(n, is2024, 5) if rng.rand() < 0.3 else None
@@ -90,7 +92,9 @@ def case_scramble():
 
 def case_seeded():
 	cube.set_is2024(bool(rng.rand() < 0.8))
-	n, depth = min(rand_n(), 3000), int(rng.choice([0, 1, 2, 3, 4, 5, 24, 25, 26, 99, 100, 101, rng.randint(1, 300)]))
+	n, depth = min(rand_n(), 3000), int(rng.choice([0, 1, 2, 3, 4, 5, 24, 25, 26, 99, 100, 101, rng.randint(1, 300), rng.randint(300, 1000)]))
+	if depth > 300:
+		n = min(n, 700)
 	sd, first = int(rng.randint(0, 2 ** 31)), int(rng.choice([0, 1, 2 ** 32 - 5, rng.randint(0, 2 ** 40)]))
 	got = cube.scramble_seeded(n, depth, sd, first)
 	acts = O.seeded_actions(sd, first, n, depth)
